@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- pair.sites/s through the Phyloformer forward on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 200x1000] [--precision bf16x3]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference algorithm on the host CPU cores
+
+One "step" = one full forward (pair embedding -> 6 axial blocks -> distance head) of one
+synthetic MSA batch.  Default workload: BASELINE config 3, one 200-taxon x 1000-site MSA
+(19 900 pairs, 19.9 M pair.sites, 5.1 GB of fp32 activations -- far larger than L2, so no
+flush is needed between steps).  With N > 1 the pair axis of the SAME MSA is sharded over the
+ranks (one all-reduce of (L,72) floats per block + one gather of the distances), i.e. strong
+scaling.  Prints ONE JSON line (rank 0).
+
+  value      device-timed throughput, MSA codes already resident in HBM (forward_idx)
+  e2e        the same metric through the reference-facing call: host (pinned) fp32 one-hot
+             (B,22,L,n) -> .cuda() -> model(x) -> .cpu(), copies inside the timed region
+  roofline   the dominant kernel (column-apply + LN + FFN + residual), timed live with CUDA
+             events around each launch (pf_profile_*), against MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle (a torch-CPU restatement of the reference graph: "port") on a
+             bounded sample of the same workload, on this box's host cores
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "pair_sites_per_s"
+UNIT = "pair*sites/s"
+FLOP_PER_TOKEN_FFN = 65536.0          # 2*(64*256 + 256*64)            SURVEY 8(a)
+BYTES_PER_TOKEN_FFN = 512.0           # one fp32 read + one fp32 write of the 64-vector
+BYTES_PER_TOKEN_FORWARD = 3072.0      # 12 activation passes           SURVEY 8(d)
+WORKLOADS = {                         # name -> (B, n, L)
+    "200x1000": (1, 200, 1000),       # BASELINE config 3 (north-star target shape)
+    "50x500": (1, 50, 500),           # config 2
+    "100x500": (1, 100, 500),         # the MSAs/s shape of the metric
+    "256x20x200": (256, 20, 200),     # config 4 (batched small MSAs)
+    "500x500": (1, 500, 500),         # config 5 (needs >= 2 GPUs worth of HBM headroom: 16 GB, fits one)
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="200x1000", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default=os.environ.get("PF_PRECISION", "bf16x3"),
+                    choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def load_weights_sd():
+    import torch
+    ck = torch.load(os.path.join(ROOT, "tests", "golden", "ckpt_pf.pt"), map_location="cpu")
+    return ck
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            busy = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
+            out = {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm), "power_w_max": max(pw)}
+        return out
+
+
+# --------------------------------------------------------------------------------------------
+def cpu_oracle_rate(n, L, threads, repeats=1):
+    """pair.sites/s of the CPU oracle (fp32, torch CPU ops = what the reference runs) on one
+    n x L MSA."""
+    import torch
+    from oracle import pf_oracle
+    torch.set_num_threads(threads)
+    w = pf_oracle.strip_prefix(load_weights_sd()["state_dict"])
+    idx = pf_oracle.synth_msa(n, L, seed=1337, kind="uniform")
+    x = pf_oracle.msa_to_onehot(idx)
+    best = None
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            pf_oracle.forward(w, x, torch.float32)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return (n * (n - 1) // 2) * L / best, best
+
+
+def pick_cpu_sample(threads, budget_s):
+    """Size a sample of the workload (fewer taxa/sites, same per-token work) to ~budget_s."""
+    rate, _ = cpu_oracle_rate(16, 128, threads)             # quick probe (~0.2 s)
+    tokens = max(rate * budget_s, 2e4)
+    for n, L in ((64, 500), (48, 400), (40, 250), (30, 200), (20, 200), (16, 128)):
+        if (n * (n - 1) // 2) * L <= tokens:
+            return n, L
+    return 16, 128
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm (CPU oracle port; the reference is Python and
+    cannot travel to the GPU box) on the host cores, same metric/config keys."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    B, n, L = WORKLOADS[args.workload]
+    per_step = max(2.0, min(10.0, 200.0 / max(1, args.steps + args.warmup)))
+    sn, sL = pick_cpu_sample(threads, per_step)
+    from oracle import pf_oracle
+    torch.set_num_threads(threads)
+    w = pf_oracle.strip_prefix(load_weights_sd()["state_dict"])
+    x = pf_oracle.msa_to_onehot(pf_oracle.synth_msa(sn, sL, seed=1337, kind="uniform"))
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            pf_oracle.forward(w, x, torch.float32)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pf_oracle.forward(w, x, torch.float32)
+        dt = time.perf_counter() - t0
+    tokens = (sn * (sn - 1) // 2) * sL
+    val = tokens * args.steps / dt
+    sample = f"{sn} taxa x {sL} sites ({tokens} pair*sites per step), fp32, torch CPU ops"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"PF {args.workload} (pf.ckpt weights); CPU arm runs a bounded sample: {sample}"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    from oracle import pf_oracle  # synthetic generator + cpu_baseline leg only
+    from phyloformer_b200.model import Phyloformer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, n, L = WORKLOADS[args.workload]
+    P = n * (n - 1) // 2
+    tokens = B * P * L
+
+    ck = load_weights_sd()
+    model = Phyloformer(**ck["hyper_parameters"], precision=args.precision)
+    model.load_state_dict({k.replace("model.", ""): v for k, v in ck["state_dict"].items()
+                           if k != "model.seq2pair"}, strict=False)
+    model = model.to(dev).eval()
+    batch_sharded = world > 1 and B >= world
+    if world > 1 and not batch_sharded:
+        model.shard_pairs()
+    idx_host = pf_oracle.synth_msa(n, L, seed=1337 + n, kind="tree", B=B)
+    if batch_sharded:  # independent MSAs: replicas, no collective
+        from phyloformer_b200 import sharding
+        lo, hi = sharding.batch_range(B, rank, world)
+        idx_host = idx_host[lo:hi].contiguous()
+    idx = idx_host.to(dev)
+    x_host = pf_oracle.msa_to_onehot(idx_host).pin_memory()      # the reference-facing input
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            d = model.forward_idx(idx, squeeze=False)
+        barrier()
+        # ---- timed region 1: device-resident inputs --------------------------------------
+        model.profile_enable(True)
+        model.profile_read()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches = 0
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            d = model.forward_idx(idx, squeeze=False)
+            launches += model.last_launches
+        e1.record()
+        barrier()
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        clocks = sampler.stop() if rank == 0 else None
+        prof = model.profile_read()
+        model.profile_enable(False)
+        # ---- timed region 2: end to end through forward(x) with host buffers ---------------
+        for _ in range(2):
+            model(x_host.to(dev, non_blocking=True)).cpu()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            out = model(x_host.to(dev, non_blocking=True))
+            out_host = out.cpu()
+        e1.record()
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+        # ---- MSAs/s at 100 x 500 (second half of BASELINE.json's metric), 1 rank ------------
+        msas_per_s = None
+        if rank == 0 and world == 1:
+            i2 = pf_oracle.synth_msa(100, 500, seed=1437).to(dev)
+            for _ in range(3):
+                model.forward_idx(i2)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(10):
+                model.forward_idx(i2)
+            e1.record()
+            torch.cuda.synchronize()
+            msas_per_s = 10 / (e0.elapsed_time(e1) * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    ms_step = ms_total / args.steps
+    value = tokens / (ms_step * 1e-3)
+    local_tokens = tokens / world
+    # dominant kernel: column-apply + LN + FFN + residual, one launch per block
+    ffn_ms, ffn_n = prof["ffn"]
+    ffn_avg = ffn_ms / max(ffn_n, 1)
+    kernels = {}
+    for k, (ms, cnt) in prof.items():
+        if cnt:
+            kernels[k] = {"ms_per_step": ms / args.steps, "launches_per_step": cnt / args.steps}
+    share = ffn_ms / args.steps / ms_step if ms_step > 0 else None
+    if args.precision == "fp32":
+        gbs = local_tokens * BYTES_PER_TOKEN_FFN / (ffn_avg * 1e-3) / 1e9
+        roofline = {"kernel": "k_colapply_ffn_fp32", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
+                    "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+                    "note": "fp32 FFMA mode is CUDA-core bound; HBM figure given for reference"}
+    else:
+        issued = 3.0 if args.precision == "bf16x3" else 1.0
+        tf = local_tokens * FLOP_PER_TOKEN_FFN / (ffn_avg * 1e-3) / 1e12
+        peak = peaks["bf16_tflops_sustained"]
+        roofline = {"kernel": "k_colapply_ffn_tc", "bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s",
+                    "frac": tf / peak, "traffic": None, "achieved_issued": tf * issued, "frac_issued": tf * issued / peak,
+                    "hbm_gbs": local_tokens * BYTES_PER_TOKEN_FFN / (ffn_avg * 1e-3) / 1e9,
+                    "note": f"useful FLOPs = 65536/token; {int(issued)} bf16 MMA passes issued per product"}
+    roofline.update({"peak_source": peaks["source"] + " (sustained)" if roofline["bound"] == "tensor" else peaks["source"],
+                     "avg_launch_ms": ffn_avg, "share_of_step": share, "kernels": kernels,
+                     "forward_hbm_frac_at_3072B": value * BYTES_PER_TOKEN_FORWARD / 1e9 / peaks["hbm_gbs"] / world})
+
+    h2d = x_host.numel() * 4
+    d2h = out_host.numel() * out_host.element_size()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak" if batch_sharded else "strong", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "bf16x3": "f32 (FFN: bf16x3 tcgen05, f32 accumulate)", "bf16": "f32 (FFN: bf16 tcgen05)"}[args.precision],
+        "data": "synthetic",
+        "config": {"workload": f"PF {args.workload}: B={B} MSAs of {n} taxa x {L} sites, {P} pairs each, pf.ckpt weights",
+                   "tokens_per_step": tokens, "precision": args.precision,
+                   "parallelism": ("1 GPU" if world == 1 else (f"batch-sharded x{world} (replicas)" if batch_sharded
+                                                               else f"pair-sharded x{world}, all-reduce of (L,72) fp32 per block")),
+                   "l2": "activations (%.2f GB per rank) exceed L2; no flush needed" % (local_tokens * 256 / 1e9)},
+        "clocks": clocks,
+        "e2e": {"value": tokens / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+                "api": "Phyloformer.forward(x: (B,22,L,n) fp32 one-hot from pinned host memory).cpu()"},
+        "gpu_launches": launches,
+        "roofline": roofline,
+    }
+    if msas_per_s is not None:
+        line["msas_per_s_100x500"] = msas_per_s
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sn, sL = pick_cpu_sample(threads, 15.0)
+        rate, secs = cpu_oracle_rate(sn, sL, threads)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"{sn} taxa x {sL} sites, one forward, {secs:.1f} s, fp32 torch CPU ops"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)

@@ -1,0 +1,136 @@
+/* pf_sm100.h -- C ABI of libpf_sm100.so, the sm_100a implementation of the Phyloformer
+ * inference hot path (MSA -> pairwise evolutionary distances).
+ *
+ * The reference (lucanest/Phyloformer) has no FFI layer: its boundary for this path is the
+ * Python surface `phyloformer.model.Phyloformer.forward(x)` (reference phyloformer/model.py:
+ * 166-187).  `phyloformer_b200/model.py` keeps that surface and calls the entry points below
+ * through ctypes; INTEGRATION.md shows the binding.  Each entry point names the reference
+ * code it replaces.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only, no C++/torch types; nothing throws across the ABI.
+ *   - every `*_dev` pointer is CALLER-OWNED DEVICE memory on the current CUDA device; the
+ *     library allocates only its packed copy of the weights (pf_create / pf_destroy).
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no hidden
+ *     synchronisation (pf_create is the one exception: it copies and repacks the weights).
+ *   - return value 0 = success, negative = error; pf_last_error() gives the message
+ *     (thread-local).
+ *   - pair order is the reference's lexicographic (i<j) order (model.py:13-17); a shard
+ *     owns the contiguous pair range [pair_lo, pair_hi).
+ */
+#ifndef PF_SM100_H
+#define PF_SM100_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PF_ABI_VERSION 1
+
+/* arithmetic of the FFN contraction (the only dense GEMM on the path) */
+#define PF_PREC_FP32   0 /* fp32 FFMA everywhere ("exact" mode, ~1e-6 of the reference)      */
+#define PF_PREC_BF16X3 1 /* tcgen05 bf16 MMAs, 3-term hi/lo split, fp32 accumulate in TMEM   */
+#define PF_PREC_BF16   2 /* single bf16 tcgen05 pass (fast mode, reported separately)        */
+
+#define PF_OK              0
+#define PF_ERR_ARG        -1
+#define PF_ERR_CUDA       -2
+#define PF_ERR_WORKSPACE  -3
+#define PF_ERR_NO_DEVICE  -4 /* no sm_100 device: there is no CPU fallback */
+#define PF_ERR_REDUCE     -5
+
+/* number of fp32 values exchanged per (MSA, site) per block between pair shards:
+ * sum_p k~ (4), sum_p q~ (4), sum_p k~ * v (64)    (attention.py:179-190 before normalising) */
+#define PF_COLSUM_FLOATS 72
+/* number of weight tensors, in reference state-dict order */
+#define PF_N_WEIGHTS(nb) (2 + 26 * (nb) + 2)
+
+typedef struct pf_ctx* pf_handle;
+
+typedef struct {
+  int32_t nb_blocks; /* 6  */
+  int32_t nb_heads;  /* 4  (only 4 is built)  */
+  int32_t embed_dim; /* 64 (only 64 is built) */
+  int32_t ffn_mult;  /* 4  */
+  int32_t precision; /* PF_PREC_* */
+} pf_cfg;
+
+/* Sums `count` fp32 values at `buf_dev` in place over all pair shards, enqueued on `stream`.
+ * Called once per block (column attention, reference model.py:97) when a forward covers only
+ * part of the pair list.  Return 0 on success. */
+typedef int (*pf_reduce_fn)(void* user, float* buf_dev, size_t count, void* stream);
+
+/* Replaces Phyloformer.__init__ + load_state_dict (model.py:112-164, infer_alns.py:71-86):
+ * takes the 160 fp32 weight tensors as device pointers in state-dict order
+ *   embedding_block.0.{weight,bias};
+ *   attention_blocks.i.{row_attention,col_attention}.{k_proj,q_proj,v_proj,out_proj}.{weight,bias},
+ *   attention_blocks.i.{row_norm,col_norm,ffn_norm}.{weight,bias},
+ *   attention_blocks.i.ffn.{0,3}.{weight,bias};   pwFNN.0.{weight,bias}
+ * and builds the packed device copy the kernels read. Synchronous. */
+int pf_create(pf_handle* out, const pf_cfg* cfg, const float* const* weights_dev, int n_weights);
+void pf_destroy(pf_handle h);
+
+/* Change the FFN arithmetic of an existing handle (PF_PREC_*). */
+int pf_set_precision(pf_handle h, int precision);
+
+/* Bytes of scratch pf_forward needs for B MSAs of n taxa x L sites, pairs [pair_lo,pair_hi). */
+size_t pf_workspace_bytes(pf_handle h, int B, int n, int L, int64_t pair_lo, int64_t pair_hi);
+
+/* Replaces data.py:28-29 + infer_alns.py:112 on the device side: (B,22,L,n) fp32 one-hot ->
+ * (B,n,L) uint8 residue codes.  *not_onehot_dev is set to 1 if any column is not exactly
+ * one-hot (the forward then uses the general embedding path on x itself). */
+int pf_onehot_to_idx(const float* x_dev, int B, int L, int n, uint8_t* idx_dev,
+                     int32_t* not_onehot_dev, void* stream);
+
+/* Replaces Phyloformer.forward (model.py:166-187) for pairs [pair_lo, pair_hi):
+ *   msa_idx_dev     (B,n,L) uint8 residue codes 0..21 (ALPHABET order, data.py:7)
+ *   x_dev           NULL, or the (B,22,L,n) fp32 input; used instead of msa_idx_dev when
+ *                   *not_onehot_dev != 0 (soft inputs keep forward(x)'s semantics)
+ *   not_onehot_dev  NULL (treated as 0) or the flag written by pf_onehot_to_idx
+ *   dist_dev        (B, pair_hi-pair_lo) fp32 out: mean_l softplus(pwFNN(.)) (model.py:182-185)
+ *   ws_dev/ws_bytes scratch of at least pf_workspace_bytes()
+ *   reduce          NULL when the shard holds all n(n-1)/2 pairs, else the cross-shard sum */
+int pf_forward(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev,
+               const int32_t* not_onehot_dev, int B, int n, int L, int64_t pair_lo,
+               int64_t pair_hi, float* dist_dev, void* ws_dev, size_t ws_bytes, void* stream,
+               pf_reduce_fn reduce, void* reduce_user);
+
+/* Test hook: same as pf_forward but stops after `n_stages` sub-blocks (stage 0 = pair
+ * embedding, then row, col, ffn per block) and copies the (B,Pl,L,64) activation to act_dev. */
+int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev,
+                     const int32_t* not_onehot_dev, int B, int n, int L, int64_t pair_lo,
+                     int64_t pair_hi, float* dist_dev, void* ws_dev, size_t ws_bytes,
+                     void* stream, pf_reduce_fn reduce, void* reduce_user, int n_stages,
+                     float* act_dev);
+
+/* Replaces infer_alns.py:14-25 (vec_to_phylip's triu scatter + dm + dm.T):
+ * (B,P) distances -> (B,n,n) symmetric matrices with a zero diagonal. */
+int pf_dist_to_matrix(const float* dist_dev, int B, int n, float* mat_dev, void* stream);
+
+/* Kernel launches enqueued by the last pf_forward on this handle (for bench.py's
+ * gpu_launches claim). */
+int pf_last_launch_count(pf_handle h);
+
+/* Per-kernel device timing (bench.py's roofline leg): when enabled, pf_forward brackets every
+ * kernel launch with CUDA events on `stream`.  pf_profile_read waits for them and returns, per
+ * kernel class, the summed milliseconds and the number of launches since the last read. */
+#define PF_KC_INPUT 0   /* one-hot conversion / sequence embedding            */
+#define PF_KC_ROW 1     /* pair embedding + row attention                      */
+#define PF_KC_COLSUM 2  /* column partial sums                                 */
+#define PF_KC_COLFIN 3  /* column reduce + finalize (tiny)                     */
+#define PF_KC_FFN 4     /* column apply + LayerNorm + FFN + residual           */
+#define PF_KC_HEAD 5    /* distance head                                       */
+#define PF_KC_COUNT 6
+int pf_profile_enable(pf_handle h, int on);
+int pf_profile_read(pf_handle h, float* ms_out /*[PF_KC_COUNT]*/, int32_t* launches_out /*[PF_KC_COUNT]*/);
+
+int pf_abi_version(void);
+const char* pf_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PF_SM100_H */

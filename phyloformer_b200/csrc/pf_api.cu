@@ -1,0 +1,444 @@
+// pf_api.cu -- the C ABI of libpf_sm100.so (see include/pf_sm100.h) and the host-side
+// orchestration of one Phyloformer forward: which kernels run, in which order, on which
+// buffers.  No torch, no NCCL: device memory and the cross-shard sum come from the caller.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pf_sm100.h"
+#include "pf_common.cuh"
+#include "pf_kernels.cuh"
+#include "pf_ffn_tc.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t e_ = (expr);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(PF_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, \
+                  __LINE__);                                                                  \
+  } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Plan {  // workspace carve-up for one (B, n, L, pair range)
+  long long Pl, P;
+  int n_chunks, ppc;
+  size_t off_x, off_part, off_colsum, off_colM, off_semb, total;
+};
+
+}  // namespace
+
+struct pf_ctx {
+  pf_cfg cfg;
+  int n_sm = 0;
+  PfHeadW* head_dev = nullptr;
+  PfBlockW* blk_dev = nullptr;  // [nb]
+  PfFfnTcW* tc_dev = nullptr;   // [nb] bf16 hi/lo smem images for the tcgen05 FFN
+  int launches = 0;
+  // optional per-kernel timing (pf_profile_*)
+  bool prof = false;
+  struct Rec { int kc; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get_event() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+};
+
+namespace {
+// RAII bracket around one kernel launch
+struct Timed {
+  pf_ctx* h; cudaStream_t st; int idx = -1;
+  Timed(pf_ctx* h_, int kc, cudaStream_t st_) : h(h_), st(st_) {
+    ++h->launches;
+    if (h->prof) {
+      pf_ctx::Rec r{kc, h->get_event(), h->get_event()};
+      cudaEventRecord(r.a, st);
+      h->recs.push_back(r);
+      idx = (int)h->recs.size() - 1;
+    }
+  }
+  ~Timed() { if (idx >= 0) cudaEventRecord(h->recs[idx].b, st); }
+};
+}  // namespace
+
+namespace {
+
+Plan make_plan(const pf_ctx* h, int B, int n, int L, long long lo, long long hi) {
+  Plan p;
+  p.P = (long long)n * (n - 1) / 2;
+  p.Pl = hi - lo;
+  const int site_tiles = (L + 31) / 32;
+  const long long want = (long long)h->n_sm * 4;
+  long long nc = (want + (long long)site_tiles * B - 1) / ((long long)site_tiles * B);
+  if (nc < 1) nc = 1;
+  if (nc > p.Pl) nc = p.Pl > 0 ? p.Pl : 1;
+  p.ppc = (int)((p.Pl + nc - 1) / nc);
+  if (p.ppc < 1) p.ppc = 1;
+  p.n_chunks = (int)((p.Pl + p.ppc - 1) / p.ppc);
+  if (p.n_chunks < 1) p.n_chunks = 1;
+  size_t off = 0;
+  p.off_x = off;       off = align_up(off + (size_t)B * p.Pl * L * PF_D * sizeof(float), 256);
+  p.off_part = off;    off = align_up(off + (size_t)p.n_chunks * B * L * PF_PART * sizeof(float), 256);
+  p.off_colsum = off;  off = align_up(off + (size_t)B * L * PF_COLSUM * sizeof(float), 256);
+  p.off_colM = off;    off = align_up(off + (size_t)B * L * PF_MROW * sizeof(float), 256);
+  p.off_semb = off;    off = align_up(off + (size_t)B * n * L * PF_D * sizeof(float), 256);
+  p.total = off;
+  return p;
+}
+
+// ---- host-side weight packing ---------------------------------------------------------------
+struct HostW {
+  std::vector<std::vector<float>> t;  // tensors in state-dict order
+};
+
+void pack_attn(const HostW& w, int base, int ln_base, PfAttnW* o) {
+  const float* kw = w.t[base + 0].data(); const float* kb = w.t[base + 1].data();
+  const float* qw = w.t[base + 2].data(); const float* qb = w.t[base + 3].data();
+  const float* vw = w.t[base + 4].data(); const float* vb = w.t[base + 5].data();
+  const float* ow = w.t[base + 6].data(); const float* ob = w.t[base + 7].data();
+  const float* g = w.t[ln_base].data();   const float* be = w.t[ln_base + 1].data();
+  for (int v = 0; v < 8; ++v) {
+    const float* src = v < 4 ? kw + v * PF_D : qw + (v - 4) * PF_D;
+    double acc = v < 4 ? kb[v] : qb[v - 4];
+    for (int c = 0; c < PF_D; ++c) {
+      o->wqk[v][c] = (float)((double)src[c] * (double)g[c]);
+      acc += (double)src[c] * (double)be[c];
+    }
+    o->bqk[v] = (float)acc;
+  }
+  for (int c = 0; c < PF_D; ++c) {
+    o->gamma[c] = g[c];
+    o->beta[c] = be[c];
+    o->bv[c] = vb[c];
+    o->bo[c] = ob[c];
+    for (int k = 0; k < PF_D; ++k) {
+      o->wvT[k][c] = vw[c * PF_D + k];
+      o->wo[c][k] = ow[c * PF_D + k];
+    }
+  }
+}
+
+void pack_ffn(const HostW& w, int base, int ln_base, PfFfnW* o) {
+  const float* w1 = w.t[base + 0].data(); const float* b1 = w.t[base + 1].data();  // (256,64)
+  const float* w2 = w.t[base + 2].data(); const float* b2 = w.t[base + 3].data();  // (64,256)
+  const float* g = w.t[ln_base].data();   const float* be = w.t[ln_base + 1].data();
+  for (int jj = 0; jj < PF_HID; ++jj) {
+    double acc = b1[jj];
+    for (int k = 0; k < PF_D; ++k) {
+      o->w1T[k][jj] = (float)((double)w1[jj * PF_D + k] * (double)g[k]);
+      acc += (double)w1[jj * PF_D + k] * (double)be[k];
+    }
+    o->b1[jj] = (float)acc;
+    for (int c = 0; c < PF_D; ++c) o->w2T[jj][c] = w2[c * PF_HID + jj];
+  }
+  for (int c = 0; c < PF_D; ++c) o->b2[c] = b2[c];
+}
+
+}  // namespace
+
+extern "C" {
+
+int pf_abi_version(void) { return PF_ABI_VERSION; }
+const char* pf_last_error(void) { return g_err; }
+
+int pf_create(pf_handle* out, const pf_cfg* cfg, const float* const* weights_dev, int n_weights) {
+  if (!out || !cfg || !weights_dev) return fail(PF_ERR_ARG, "pf_create: null argument");
+  if (cfg->nb_heads != PF_H || cfg->embed_dim != PF_D || cfg->ffn_mult != 4 || cfg->nb_blocks < 1)
+    return fail(PF_ERR_ARG, "pf_create: only nb_heads=4, embed_dim=64, ffn_mult=4 are built (got %d,%d,%d)",
+                cfg->nb_heads, cfg->embed_dim, cfg->ffn_mult);
+  const int nb = cfg->nb_blocks;
+  if (n_weights != PF_N_WEIGHTS(nb))
+    return fail(PF_ERR_ARG, "pf_create: expected %d weight tensors, got %d", PF_N_WEIGHTS(nb), n_weights);
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(PF_ERR_NO_DEVICE, "pf_create: no CUDA device (there is no CPU fallback)");
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return fail(PF_ERR_NO_DEVICE, "pf_create: device %s is sm_%d%d; this library is built for sm_100a only",
+                prop.name, prop.major, prop.minor);
+
+  // sizes in state-dict order
+  std::vector<size_t> sz;
+  sz.push_back((size_t)PF_D * PF_NCHAR); sz.push_back(PF_D);
+  for (int b = 0; b < nb; ++b) {
+    for (int a = 0; a < 2; ++a) {
+      sz.push_back(PF_H * PF_D); sz.push_back(PF_H); sz.push_back(PF_H * PF_D); sz.push_back(PF_H);
+      sz.push_back(PF_D * PF_D); sz.push_back(PF_D); sz.push_back(PF_D * PF_D); sz.push_back(PF_D);
+    }
+    for (int i = 0; i < 6; ++i) sz.push_back(PF_D);
+    sz.push_back((size_t)PF_HID * PF_D); sz.push_back(PF_HID);
+    sz.push_back((size_t)PF_D * PF_HID); sz.push_back(PF_D);
+  }
+  sz.push_back(PF_D); sz.push_back(1);
+  HostW hw;
+  hw.t.resize(sz.size());
+  for (size_t i = 0; i < sz.size(); ++i) {
+    if (!weights_dev[i]) return fail(PF_ERR_ARG, "pf_create: weight %zu is null", i);
+    hw.t[i].resize(sz[i]);
+    CUDA_TRY(cudaMemcpy(hw.t[i].data(), weights_dev[i], sz[i] * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+
+  pf_ctx* h = new pf_ctx();
+  h->cfg = *cfg;
+  h->n_sm = prop.multiProcessorCount;
+
+  std::vector<PfHeadW> head(1);
+  memset(head.data(), 0, sizeof(PfHeadW));
+  {
+    const float* we = hw.t[0].data();  // (64,22)
+    const float* be = hw.t[1].data();
+    for (int a = 0; a < PF_NCHAR; ++a)
+      for (int c = 0; c < PF_D; ++c) {
+        const float v = we[c * PF_NCHAR + a] + be[c];
+        head[0].table[a][c] = v > 0.f ? v : 0.f;
+        head[0].weT[a][c] = we[c * PF_NCHAR + a];
+      }
+    for (int c = 0; c < PF_D; ++c) head[0].be[c] = be[c];
+    const size_t hb = sz.size() - 2;
+    for (int c = 0; c < PF_D; ++c) head[0].whead[c] = hw.t[hb][c];
+    head[0].bhead = hw.t[hb + 1][0];
+  }
+  std::vector<PfBlockW> blk(nb);
+  std::vector<PfFfnTcW> tc(nb);
+  for (int b = 0; b < nb; ++b) {
+    const int base = 2 + 26 * b;
+    pack_attn(hw, base + 0, base + 16, &blk[b].row);
+    pack_attn(hw, base + 8, base + 18, &blk[b].col);
+    pack_ffn(hw, base + 22, base + 20, &blk[b].ffn);
+    pf_pack_ffn_tc(blk[b].ffn, &tc[b]);
+  }
+  auto cleanup = [&]() { pf_destroy(h); };
+  cudaError_t e;
+  if ((e = cudaMalloc(&h->head_dev, sizeof(PfHeadW))) != cudaSuccess ||
+      (e = cudaMalloc(&h->blk_dev, sizeof(PfBlockW) * nb)) != cudaSuccess ||
+      (e = cudaMalloc(&h->tc_dev, sizeof(PfFfnTcW) * nb)) != cudaSuccess ||
+      (e = cudaMemcpy(h->head_dev, head.data(), sizeof(PfHeadW), cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(h->blk_dev, blk.data(), sizeof(PfBlockW) * nb, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(h->tc_dev, tc.data(), sizeof(PfFfnTcW) * nb, cudaMemcpyHostToDevice)) != cudaSuccess) {
+    cleanup();
+    return fail(PF_ERR_CUDA, "pf_create: %s", cudaGetErrorString(e));
+  }
+  // opt in to large dynamic shared memory once
+  CUDA_TRY(cudaFuncSetAttribute(k_colapply_ffn_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(Ffn32Smem)));
+  CUDA_TRY(cudaFuncSetAttribute(k_row_attn<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(k_row_attn<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  int rc = pf_ffn_tc_init();
+  if (rc != 0) { cleanup(); return fail(PF_ERR_CUDA, "pf_create: tcgen05 FFN kernel setup failed (%d)", rc); }
+  *out = h;
+  return PF_OK;
+}
+
+void pf_destroy(pf_handle h) {
+  if (!h) return;
+  if (h->head_dev) cudaFree(h->head_dev);
+  if (h->blk_dev) cudaFree(h->blk_dev);
+  if (h->tc_dev) cudaFree(h->tc_dev);
+  for (auto& r : h->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto e : h->pool) cudaEventDestroy(e);
+  delete h;
+}
+
+int pf_set_precision(pf_handle h, int precision) {
+  if (!h) return fail(PF_ERR_ARG, "pf_set_precision: null handle");
+  if (precision < PF_PREC_FP32 || precision > PF_PREC_BF16) return fail(PF_ERR_ARG, "pf_set_precision: bad mode %d", precision);
+  h->cfg.precision = precision;
+  return PF_OK;
+}
+
+size_t pf_workspace_bytes(pf_handle h, int B, int n, int L, int64_t pair_lo, int64_t pair_hi) {
+  if (!h || B < 1 || n < 2 || L < 1) return 0;
+  const long long P = (long long)n * (n - 1) / 2;
+  if (pair_lo < 0 || pair_hi > P || pair_hi < pair_lo) return 0;
+  return make_plan(h, B, n, L, pair_lo, pair_hi).total;
+}
+
+int pf_onehot_to_idx(const float* x_dev, int B, int L, int n, uint8_t* idx_dev, int32_t* not_onehot_dev,
+                     void* stream) {
+  if (!x_dev || !idx_dev || !not_onehot_dev || B < 1 || L < 1 || n < 1) return fail(PF_ERR_ARG, "pf_onehot_to_idx: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemsetAsync(not_onehot_dev, 0, sizeof(int32_t), st));
+  const long long total = (long long)B * L * n;
+  k_onehot_to_idx<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x_dev, B, L, n, idx_dev, not_onehot_dev);
+  CUDA_TRY(cudaGetLastError());
+  return PF_OK;
+}
+
+int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev, const int32_t* not_onehot_dev,
+                     int B, int n, int L, int64_t pair_lo, int64_t pair_hi, float* dist_dev, void* ws_dev,
+                     size_t ws_bytes, void* stream, pf_reduce_fn reduce, void* reduce_user, int n_stages,
+                     float* act_dev) {
+  if (!h) return fail(PF_ERR_ARG, "pf_forward: null handle");
+  if (!msa_idx_dev || !ws_dev) return fail(PF_ERR_ARG, "pf_forward: null buffer");
+  if (B < 1 || n < 2 || L < 1) return fail(PF_ERR_ARG, "pf_forward: need B>=1, n>=2, L>=1 (got %d,%d,%d)", B, n, L);
+  const long long P = (long long)n * (n - 1) / 2;
+  if (pair_lo < 0 || pair_hi > P || pair_hi <= pair_lo)
+    return fail(PF_ERR_ARG, "pf_forward: bad pair range [%lld,%lld) of %lld", (long long)pair_lo, (long long)pair_hi, P);
+  if ((pair_hi - pair_lo) != P && reduce == nullptr)
+    return fail(PF_ERR_ARG, "pf_forward: a partial pair range needs a reduce callback");
+  if (!dist_dev && n_stages < 0) return fail(PF_ERR_ARG, "pf_forward: null dist buffer");
+  const Plan pl = make_plan(h, B, n, L, pair_lo, pair_hi);
+  if (ws_bytes < pl.total) return fail(PF_ERR_WORKSPACE, "pf_forward: workspace %zu < %zu bytes", ws_bytes, pl.total);
+  if ((long long)B * pl.Pl > 0x7fffffffLL) return fail(PF_ERR_ARG, "pf_forward: too many pair rows");
+  const size_t row_smem = sizeof(RowSmem) + (size_t)L * 4 * sizeof(float);
+  if (row_smem > 200 * 1024) return fail(PF_ERR_ARG, "pf_forward: L=%d exceeds the row kernel's shared-memory budget", L);
+
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* ws = (unsigned char*)ws_dev;
+  float* x = (float*)(ws + pl.off_x);
+  float* part = (float*)(ws + pl.off_part);
+  float* colsum = (float*)(ws + pl.off_colsum);
+  float* colM = (float*)(ws + pl.off_colM);
+  float* semb = (float*)(ws + pl.off_semb);
+  const int rows = (int)(B * pl.Pl);
+  const long long n_tok = (long long)rows * L;
+  const int nb = h->cfg.nb_blocks;
+  const bool dbg = n_stages >= 0;
+  int stage = 0;
+  h->launches = 0;
+  auto done = [&]() -> int {
+    if (dbg && act_dev) {
+      cudaError_t e = cudaMemcpyAsync(act_dev, x, (size_t)n_tok * PF_D * sizeof(float), cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) return fail(PF_ERR_CUDA, "debug copy: %s", cudaGetErrorString(e));
+    }
+    return PF_OK;
+  };
+
+  if (x_dev != nullptr && not_onehot_dev != nullptr) {
+    const long long tot = (long long)B * n * L * PF_D;
+    Timed t_(h, PF_KC_INPUT, st);
+    k_embed_sequences<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(h->head_dev, x_dev, not_onehot_dev, B, L, n, semb);
+  }
+  const int* flag = (x_dev != nullptr) ? not_onehot_dev : nullptr;
+
+  for (int b = 0; b < nb; ++b) {
+    const PfBlockW* bw = h->blk_dev + b;
+    // ---- row attention (block 0: fused with the pair embedding) ----
+    if (b == 0) {
+      const int embed_only = (dbg && n_stages == 0) ? 1 : 0;
+      {
+        Timed t_(h, PF_KC_ROW, st);
+        k_row_attn<1><<<rows, 256, row_smem, st>>>(&bw->row, h->head_dev, x, msa_idx_dev, semb, flag, n, L, pair_lo,
+                                                   (int)pl.Pl, embed_only);
+      }
+      CUDA_TRY(cudaGetLastError());
+      if (embed_only) return done();
+    } else {
+      Timed t_(h, PF_KC_ROW, st);
+      k_row_attn<0><<<rows, 256, row_smem, st>>>(&bw->row, h->head_dev, x, nullptr, nullptr, nullptr, n, L, pair_lo,
+                                                 (int)pl.Pl, 0);
+    }
+    CUDA_TRY(cudaGetLastError());
+    stage = 3 * b + 1;
+    if (dbg && stage == n_stages) return done();
+    // ---- column attention summaries ----
+    {
+      dim3 g((L + 31) / 32, pl.n_chunks, B);
+      {
+        Timed t_(h, PF_KC_COLSUM, st);
+        k_col_partial<<<g, 256, 0, st>>>(&bw->col, x, part, L, (int)pl.Pl, pl.ppc);
+      }
+      dim3 g2(L, B);
+      {
+        Timed t_(h, PF_KC_COLFIN, st);
+        k_col_reduce<<<g2, 64, 0, st>>>(&bw->col, part, pl.n_chunks, L, colsum);
+      }
+      CUDA_TRY(cudaGetLastError());
+      if (reduce) {
+        const int rc = reduce(reduce_user, colsum, (size_t)B * L * PF_COLSUM, stream);
+        if (rc != 0) return fail(PF_ERR_REDUCE, "pf_forward: reduce callback returned %d", rc);
+      }
+      {
+        Timed t_(h, PF_KC_COLFIN, st);
+        k_col_finalize<<<g2, 256, 0, st>>>(&bw->col, colsum, (float)P, L, colM);
+      }
+      CUDA_TRY(cudaGetLastError());
+    }
+    // ---- column apply + FFN ----
+    const bool apply_only = dbg && (n_stages == 3 * b + 2);
+    if (h->cfg.precision == PF_PREC_FP32 || apply_only) {
+      long long tiles = (n_tok + FFN32_T - 1) / FFN32_T;
+      const int grid = (int)(tiles < h->n_sm ? tiles : h->n_sm);
+      Timed t_(h, PF_KC_FFN, st);
+      k_colapply_ffn_fp32<<<grid, 256, sizeof(Ffn32Smem), st>>>(&bw->col, &bw->ffn, x, colM, L, (int)pl.Pl, n_tok,
+                                                               apply_only ? 1 : 0);
+    } else {
+      Timed t_(h, PF_KC_FFN, st);
+      const int rc = pf_ffn_tc_launch(&bw->col, h->tc_dev + b, x, colM, L, (int)pl.Pl, n_tok, h->n_sm,
+                                      h->cfg.precision == PF_PREC_BF16 ? 1 : 3, st);
+      if (rc != 0) return fail(PF_ERR_CUDA, "pf_forward: tcgen05 FFN launch failed (%d)", rc);
+    }
+    CUDA_TRY(cudaGetLastError());
+    if (apply_only) return done();
+    stage = 3 * b + 3;
+    if (dbg && stage == n_stages) return done();
+  }
+  {
+    Timed t_(h, PF_KC_HEAD, st);
+    k_head<<<rows, 256, 0, st>>>(h->head_dev, x, L, dist_dev);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return done();
+}
+
+int pf_forward(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev, const int32_t* not_onehot_dev, int B,
+               int n, int L, int64_t pair_lo, int64_t pair_hi, float* dist_dev, void* ws_dev, size_t ws_bytes,
+               void* stream, pf_reduce_fn reduce, void* reduce_user) {
+  if (!dist_dev) return fail(PF_ERR_ARG, "pf_forward: null dist buffer");
+  return pf_forward_debug(h, msa_idx_dev, x_dev, not_onehot_dev, B, n, L, pair_lo, pair_hi, dist_dev, ws_dev,
+                          ws_bytes, stream, reduce, reduce_user, -1, nullptr);
+}
+
+int pf_dist_to_matrix(const float* dist_dev, int B, int n, float* mat_dev, void* stream) {
+  if (!dist_dev || !mat_dev || B < 1 || n < 2) return fail(PF_ERR_ARG, "pf_dist_to_matrix: bad argument");
+  const long long P = (long long)n * (n - 1) / 2;
+  dim3 g((unsigned)(((long long)n * n + 255) / 256), B);
+  k_dist_to_matrix<<<g, 256, 0, (cudaStream_t)stream>>>(dist_dev, n, P, mat_dev);
+  CUDA_TRY(cudaGetLastError());
+  return PF_OK;
+}
+
+int pf_last_launch_count(pf_handle h) { return h ? h->launches : 0; }
+
+int pf_profile_enable(pf_handle h, int on) {
+  if (!h) return fail(PF_ERR_ARG, "pf_profile_enable: null handle");
+  h->prof = on != 0;
+  return PF_OK;
+}
+
+int pf_profile_read(pf_handle h, float* ms_out, int32_t* launches_out) {
+  if (!h || !ms_out || !launches_out) return fail(PF_ERR_ARG, "pf_profile_read: null argument");
+  for (int i = 0; i < PF_KC_COUNT; ++i) { ms_out[i] = 0.f; launches_out[i] = 0; }
+  for (auto& r : h->recs) {
+    CUDA_TRY(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
+    ms_out[r.kc] += ms;
+    ++launches_out[r.kc];
+    h->pool.push_back(r.a);
+    h->pool.push_back(r.b);
+  }
+  h->recs.clear();
+  return PF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,625 @@
+// pf_kernels.cuh -- CUDA-core kernels of the Phyloformer forward path (sm_100a):
+//   k_onehot_to_idx, k_embed_sequences   input conversion            (data.py:28-29, model.py:173)
+//   k_row_attn<MODE>                     pair embedding + row attention, in place (model.py:175, 90-92)
+//   k_col_partial, k_col_reduce, k_col_finalize   column attention summaries      (model.py:96-97)
+//   k_colapply_ffn_fp32                  column apply + FFN, fp32 FFMA            (model.py:97-104)
+//   k_head                               pwFNN + softplus + site mean             (model.py:182-185)
+// All of them are HBM-bound streaming kernels except the FFN contraction; see DESIGN.md.
+#pragma once
+#include "pf_common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// (B,22,L,n) fp32 one-hot -> (B,n,L) uint8 codes; sets *flag if some column is not one-hot.
+// ------------------------------------------------------------------------------------------
+__global__ void k_onehot_to_idx(const float* __restrict__ x, int B, int L, int n,
+                                uint8_t* __restrict__ idx, int* __restrict__ flag) {
+  const long long total = (long long)B * L * n;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int i = (int)(t % n);
+  const int l = (int)((t / n) % L);
+  const int b = (int)(t / ((long long)n * L));
+  const float* px = x + ((long long)b * PF_NCHAR * L + l) * n + i;
+  int code = 0, ones = 0, other = 0;
+#pragma unroll
+  for (int c = 0; c < PF_NCHAR; ++c) {
+    const float v = px[(long long)c * L * n];
+    if (v == 1.0f) { code = c; ++ones; }
+    else if (v != 0.0f) ++other;
+  }
+  idx[((long long)b * n + i) * L + l] = (uint8_t)code;
+  if (ones != 1 || other != 0) *flag = 1;  // benign race: every writer stores 1
+}
+
+// Soft-input path: E[b][i][l][:] = relu(W_e x[b,:,l,i] + b_e)      (model.py:138-143,173)
+// Skipped (early exit) when the input was one-hot.
+__global__ void k_embed_sequences(const PfHeadW* __restrict__ hw, const float* __restrict__ x,
+                                  const int* __restrict__ flag, int B, int L, int n,
+                                  float* __restrict__ emb) {
+  if (flag == nullptr || *flag == 0) return;
+  const long long total = (long long)B * n * L * PF_D;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c = (int)(t % PF_D);
+  const int l = (int)((t / PF_D) % L);
+  const int i = (int)((t / ((long long)PF_D * L)) % n);
+  const int b = (int)(t / ((long long)PF_D * L * n));
+  float acc = hw->be[c];
+#pragma unroll
+  for (int a = 0; a < PF_NCHAR; ++a)
+    acc = fmaf(hw->weT[a][c], x[(((long long)b * PF_NCHAR + a) * L + l) * n + i], acc);
+  emb[t] = fmaxf(acc, 0.f);
+}
+
+// ------------------------------------------------------------------------------------------
+// Row attention over one pair-row (attends along the L sites of a pair), in place:
+//   x[b,p,l,:] += out_proj( qhat_l * ctx )          attention.py:160-197 with R=P, N=L
+// collapsed as in SURVEY.md section 3.2:  ctx_h = Wv[h](sum_l khat_l u_l) + bv[h],  y_l = M qhat_l + bo
+// with M[:,h] = Wo[:,h-slice] ctx_h.   One CTA per (msa, pair); 32 token slots x 8 lanes.
+// MODE 0: x is read from HBM.   MODE 1: x0 = pair embedding, computed on the fly from the
+// uint8 MSA (table lookup) or, for soft inputs, from the per-sequence embedding E.
+// Phase A: LN, q/k, per-row sums.  Finalize: M, qinv.  Phase B: apply + residual, write x.
+// ------------------------------------------------------------------------------------------
+struct RowSmem {
+  float red[8][PF_PART];   // per-warp partial sums
+  float tot[PF_PART];
+  float ubar[PF_H][PF_D];
+  float ctx[PF_D];
+  float M[PF_D][PF_H];
+  float qinv[PF_H];
+  float table[PF_NCHAR][PF_D];
+};
+
+template <int MODE>
+__device__ __forceinline__ void row_fetch(const float* __restrict__ xrow, const RowSmem& sm,
+                                          const uint8_t* __restrict__ si, const uint8_t* __restrict__ sj,
+                                          const float* __restrict__ ei, const float* __restrict__ ej,
+                                          bool soft, int l, int j, float (&x)[8]) {
+  if (MODE == 0) {
+    load_tok(xrow + (size_t)l * PF_D, j, x);
+  } else if (!soft) {
+    const int a = si[l], b = sj[l];
+    const float4 a0 = reinterpret_cast<const float4*>(sm.table[a])[j];
+    const float4 a1 = reinterpret_cast<const float4*>(sm.table[a])[8 + j];
+    const float4 b0 = reinterpret_cast<const float4*>(sm.table[b])[j];
+    const float4 b1 = reinterpret_cast<const float4*>(sm.table[b])[8 + j];
+    x[0] = a0.x + b0.x; x[1] = a0.y + b0.y; x[2] = a0.z + b0.z; x[3] = a0.w + b0.w;
+    x[4] = a1.x + b1.x; x[5] = a1.y + b1.y; x[6] = a1.z + b1.z; x[7] = a1.w + b1.w;
+  } else {
+    float u[8], w[8];
+    load_tok(ei + (size_t)l * PF_D, j, u);
+    load_tok(ej + (size_t)l * PF_D, j, w);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = u[i] + w[i];
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 2)
+k_row_attn(const PfAttnW* __restrict__ W, const PfHeadW* __restrict__ hw, float* __restrict__ x,
+           const uint8_t* __restrict__ msa, const float* __restrict__ semb,
+           const int* __restrict__ soft_flag, int n, int L, long long pair_lo, int Pl, int embed_only) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RowSmem& sm = *reinterpret_cast<RowSmem*>(smem_raw);
+  float* qcache = reinterpret_cast<float*>(smem_raw + sizeof(RowSmem));  // [L][4]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j = lane & 7, slot = tid >> 3;  // 32 token slots
+  const int row = blockIdx.x;
+  const int b = row / Pl, pl = row - b * Pl;
+  float* xrow = x + (size_t)row * L * PF_D;
+
+  const uint8_t *si = nullptr, *sj = nullptr;
+  const float *ei = nullptr, *ej = nullptr;
+  bool soft = false;
+  if (MODE == 1) {
+    int pi, pj;
+    pair_to_ij(pair_lo + pl, n, &pi, &pj);
+    soft = (soft_flag != nullptr) && (*soft_flag != 0);
+    si = msa + ((size_t)b * n + pi) * L;
+    sj = msa + ((size_t)b * n + pj) * L;
+    if (soft) {
+      ei = semb + ((size_t)b * n + pi) * L * PF_D;
+      ej = semb + ((size_t)b * n + pj) * L * PF_D;
+    } else {
+      for (int t = tid; t < PF_NCHAR * PF_D; t += 256) (&sm.table[0][0])[t] = (&hw->table[0][0])[t];
+    }
+    __syncthreads();
+  }
+
+  // folded q/k weights for this lane's 8 channels
+  float wqk[8][8];
+#pragma unroll
+  for (int v = 0; v < 8; ++v) {
+    const float4 a = reinterpret_cast<const float4*>(W->wqk[v])[j];
+    const float4 c = reinterpret_cast<const float4*>(W->wqk[v])[8 + j];
+    wqk[v][0] = a.x; wqk[v][1] = a.y; wqk[v][2] = a.z; wqk[v][3] = a.w;
+    wqk[v][4] = c.x; wqk[v][5] = c.y; wqk[v][6] = c.z; wqk[v][7] = c.w;
+  }
+  const float bias_j = W->bqk[j];
+
+  // ---------------- phase A ----------------
+  float S[PF_H][8];
+#pragma unroll
+  for (int h = 0; h < PF_H; ++h)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) S[h][i] = 0.f;
+  float own = 0.f;  // lane j<4: sum k_j ; lane j>=4: sum q_{j-4}
+
+  const int n_it = (L + 31) >> 5;
+  float xn[8];
+  {
+    const int l0 = slot;
+    if (l0 < L) row_fetch<MODE>(xrow, sm, si, sj, ei, ej, soft, l0, j, xn);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xn[i] = 0.f;
+    }
+  }
+  for (int it = 0; it < n_it; ++it) {
+    const int l = it * 32 + slot;
+    const bool act = l < L;
+    float xc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xc[i] = xn[i];
+    const int ln = l + 32;
+    if (it + 1 < n_it) {
+      if (ln < L) row_fetch<MODE>(xrow, sm, si, sj, ei, ej, soft, ln, j, xn);
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xn[i] = 0.f;
+      }
+    }
+    float nv[8];
+    ln_normalize(xc, nv);
+    float part[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s = fmaf(wqk[v][i], nv[i], s);
+      part[v] = s;
+    }
+    const float mine = phi_elu1(grp_reduce8(part, j) + bias_j);
+    float kh[PF_H];
+#pragma unroll
+    for (int h = 0; h < PF_H; ++h) kh[h] = __shfl_sync(PF_FULL, mine, (lane & 24) | h);
+    if (act) {
+      own += mine;
+      if (j >= 4) qcache[(size_t)l * 4 + (j - 4)] = mine;
+#pragma unroll
+      for (int h = 0; h < PF_H; ++h)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) S[h][i] = fmaf(kh[h], nv[i], S[h][i]);
+    }
+  }
+  // reduce the 4 slots of a warp (fixed tree), then the 8 warps (fixed order)
+#pragma unroll
+  for (int h = 0; h < PF_H; ++h)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = S[h][i];
+      v += __shfl_xor_sync(PF_FULL, v, 8);
+      v += __shfl_xor_sync(PF_FULL, v, 16);
+      S[h][i] = v;
+    }
+  own += __shfl_xor_sync(PF_FULL, own, 8);
+  own += __shfl_xor_sync(PF_FULL, own, 16);
+  if (lane < 8) {
+    sm.red[warp][j] = own;
+#pragma unroll
+    for (int h = 0; h < PF_H; ++h)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sm.red[warp][8 + h * PF_D + chan_of(j, i)] = S[h][i];
+  }
+  __syncthreads();
+  for (int t = tid; t < PF_PART; t += 256) {
+    float s = sm.red[0][t];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) s += sm.red[w][t];
+    sm.tot[t] = s;
+  }
+  __syncthreads();
+  // ---------------- per-row finalize ----------------
+  if (tid < PF_D) {
+#pragma unroll
+    for (int h = 0; h < PF_H; ++h)
+      sm.ubar[h][tid] = fmaf(W->gamma[tid], sm.tot[8 + h * PF_D + tid] / sm.tot[h], W->beta[tid]);
+  }
+  __syncthreads();
+  if (tid < PF_D) {
+    const int h = tid >> 4;
+    float acc = W->bv[tid];
+#pragma unroll 8
+    for (int k = 0; k < PF_D; ++k) acc = fmaf(W->wvT[k][tid], sm.ubar[h][k], acc);
+    sm.ctx[tid] = acc;
+  }
+  if (tid < PF_H) sm.qinv[tid] = (float)L / sm.tot[4 + tid];
+  __syncthreads();
+  {
+    const int c = tid >> 2, h = tid & 3;
+    float acc = 0.f;
+#pragma unroll
+    for (int e = 0; e < PF_DH; ++e) acc = fmaf(W->wo[c][h * PF_DH + e], sm.ctx[h * PF_DH + e], acc);
+    sm.M[c][h] = acc;
+  }
+  __syncthreads();
+  // ---------------- phase B: y = x + M qhat + bo ----------------
+  float4 Mr[8];
+  float bo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = chan_of(j, i);
+    Mr[i] = *reinterpret_cast<const float4*>(sm.M[c]);
+    bo[i] = W->bo[c];
+  }
+  const float4 qi = *reinterpret_cast<const float4*>(sm.qinv);
+  for (int l = slot; l < L; l += 32) {
+    float xc[8];
+    row_fetch<MODE>(xrow, sm, si, sj, ei, ej, soft, l, j, xc);
+    float4 q = *reinterpret_cast<const float4*>(qcache + (size_t)l * 4);
+    q.x *= qi.x; q.y *= qi.y; q.z *= qi.z; q.w *= qi.w;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float a = bo[i];
+      a = fmaf(Mr[i].x, q.x, a);
+      a = fmaf(Mr[i].y, q.y, a);
+      a = fmaf(Mr[i].z, q.z, a);
+      a = fmaf(Mr[i].w, q.w, a);
+      if (!embed_only) xc[i] += a;
+    }
+    store_tok(xrow + (size_t)l * PF_D, j, xc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Column attention, step 1: partial sums over a chunk of pairs at each site.
+//   part[chunk][b][l][0:4]  = sum_p k~_h      [4:8] = sum_p q~_h      [8+64h+c] = sum_p k~_h n_c
+// (n = LN(x) without affine; k~, q~ un-normalised phi values, attention.py:179-180 with
+//  R=L, N=P).  A token slot owns one site and walks down the pairs, so there is no cross-lane
+//  reduction and the order of the sum is fixed.   grid = (ceil(L/32), n_chunks, B)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2)
+k_col_partial(const PfAttnW* __restrict__ W, const float* __restrict__ x, float* __restrict__ part,
+              int L, int Pl, int pairs_per_chunk) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int j = lane & 7, slot = tid >> 3;
+  const int l = blockIdx.x * 32 + slot;
+  const int chunk = blockIdx.y, b = blockIdx.z, B = gridDim.z;
+  const bool act = l < L;
+  const int p0 = chunk * pairs_per_chunk;
+  const int p1 = min(Pl, p0 + pairs_per_chunk);
+
+  float wqk[8][8];
+#pragma unroll
+  for (int v = 0; v < 8; ++v) {
+    const float4 a = reinterpret_cast<const float4*>(W->wqk[v])[j];
+    const float4 c = reinterpret_cast<const float4*>(W->wqk[v])[8 + j];
+    wqk[v][0] = a.x; wqk[v][1] = a.y; wqk[v][2] = a.z; wqk[v][3] = a.w;
+    wqk[v][4] = c.x; wqk[v][5] = c.y; wqk[v][6] = c.z; wqk[v][7] = c.w;
+  }
+  const float bias_j = W->bqk[j];
+  float S[PF_H][8];
+#pragma unroll
+  for (int h = 0; h < PF_H; ++h)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) S[h][i] = 0.f;
+  float own = 0.f;
+
+  const size_t pstride = (size_t)L * PF_D;
+  const float* px = x + ((size_t)b * Pl + p0) * pstride + (size_t)(act ? l : 0) * PF_D;
+  float xn[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) xn[i] = 0.f;
+  if (act && p0 < p1) load_tok(px, j, xn);
+  for (int p = p0; p < p1; ++p) {
+    float xc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xc[i] = xn[i];
+    if (act && p + 1 < p1) load_tok(px + pstride, j, xn);
+    px += pstride;
+    float nv[8];
+    ln_normalize(xc, nv);
+    float pr[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s = fmaf(wqk[v][i], nv[i], s);
+      pr[v] = s;
+    }
+    const float mine = phi_elu1(grp_reduce8(pr, j) + bias_j);
+    float kh[PF_H];
+#pragma unroll
+    for (int h = 0; h < PF_H; ++h) kh[h] = __shfl_sync(PF_FULL, mine, (lane & 24) | h);
+    own += mine;
+#pragma unroll
+    for (int h = 0; h < PF_H; ++h)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) S[h][i] = fmaf(kh[h], nv[i], S[h][i]);
+  }
+  if (act) {
+    float* o = part + (((size_t)chunk * B + b) * L + l) * PF_PART;
+    o[j] = own;
+#pragma unroll
+    for (int h = 0; h < PF_H; ++h) {
+      reinterpret_cast<float4*>(o + 8 + h * PF_D)[j] = make_float4(S[h][0], S[h][1], S[h][2], S[h][3]);
+      reinterpret_cast<float4*>(o + 8 + h * PF_D)[8 + j] = make_float4(S[h][4], S[h][5], S[h][6], S[h][7]);
+    }
+  }
+}
+
+// Column attention, step 2: fixed-order sum over the chunks, then the linear map to the
+// 72-float exchange form:  sum_p k~ v = Wv[h] (g * sum_p k~ n + b sum_p k~) + bv[h] sum_p k~.
+//   grid = (L, B), 64 threads
+__global__ void __launch_bounds__(64)
+k_col_reduce(const PfAttnW* __restrict__ W, const float* __restrict__ part, int n_chunks, int L,
+             float* __restrict__ colsum) {
+  __shared__ float ub[PF_H][PF_D];
+  __shared__ float sums[8];
+  const int t = threadIdx.x, l = blockIdx.x, b = blockIdx.y, B = gridDim.y;
+  float s[PF_H] = {0.f, 0.f, 0.f, 0.f};
+  float s8 = 0.f;
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const float* p = part + (((size_t)ch * B + b) * L + l) * PF_PART;
+#pragma unroll
+    for (int h = 0; h < PF_H; ++h) s[h] += p[8 + h * PF_D + t];
+    if (t < 8) s8 += p[t];
+  }
+  if (t < 8) sums[t] = s8;
+  __syncthreads();
+#pragma unroll
+  for (int h = 0; h < PF_H; ++h) ub[h][t] = fmaf(W->gamma[t], s[h], W->beta[t] * sums[h]);
+  __syncthreads();
+  const int h = t >> 4;
+  float acc = W->bv[t] * sums[h];
+#pragma unroll 8
+  for (int k = 0; k < PF_D; ++k) acc = fmaf(W->wvT[k][t], ub[h][k], acc);
+  float* o = colsum + ((size_t)b * L + l) * PF_COLSUM;
+  o[8 + t] = acc;
+  if (t < 8) o[t] = sums[t];
+}
+
+// Column attention, step 3 (after the cross-shard sum): ctx = kv / sum k,  M_l = Wo[:,h] ctx_h,
+// qinv = P / sum q~.     grid = (L, B), 256 threads
+__global__ void __launch_bounds__(256)
+k_col_finalize(const PfAttnW* __restrict__ W, const float* __restrict__ colsum, float p_total,
+               int L, float* __restrict__ colM) {
+  __shared__ float ctx[PF_D];
+  const int t = threadIdx.x, l = blockIdx.x, b = blockIdx.y;
+  const float* s = colsum + ((size_t)b * L + l) * PF_COLSUM;
+  float* o = colM + ((size_t)b * L + l) * PF_MROW;
+  if (t < PF_D) ctx[t] = s[8 + t] / s[t >> 4];
+  if (t < PF_H) o[256 + t] = p_total / s[4 + t];
+  __syncthreads();
+  const int c = t >> 2, h = t & 3;
+  float acc = 0.f;
+#pragma unroll
+  for (int e = 0; e < PF_DH; ++e) acc = fmaf(W->wo[c][h * PF_DH + e], ctx[h * PF_DH + e], acc);
+  o[c * 4 + h] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// Column apply + FFN, fp32 FFMA ("exact" mode and the check for the tcgen05 kernel):
+//   x2 = x1 + M_l qhat + bo ;  x3 = x2 + W2 gelu(W1 LN(x2) + b1) + b2        model.py:97-104
+// Persistent: one CTA per SM, 32-token tiles, both weight matrices resident in smem.
+// ------------------------------------------------------------------------------------------
+#define FFN32_T 32
+#define FFN32_HS (PF_HID + 4)
+struct Ffn32Smem {
+  float w1T[PF_D][PF_HID];
+  float w2T[PF_HID][PF_D];
+  float A[FFN32_T][PF_D];      // LN(x2) without affine; reused for the GEMM2 output
+  float Hid[FFN32_T][FFN32_HS];
+  float b1[PF_HID];
+  float b2[PF_D];
+};
+
+__global__ void __launch_bounds__(256, 1)
+k_colapply_ffn_fp32(const PfAttnW* __restrict__ Wc, const PfFfnW* __restrict__ Wf,
+                    float* __restrict__ x, const float* __restrict__ colM, int L, int Pl,
+                    long long n_tok, int apply_only) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Ffn32Smem& sm = *reinterpret_cast<Ffn32Smem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int j = lane & 7, slot = tid >> 3;
+
+  for (int t = tid; t < PF_D * PF_HID / 4; t += 256) {
+    reinterpret_cast<float4*>(&sm.w1T[0][0])[t] = reinterpret_cast<const float4*>(&Wf->w1T[0][0])[t];
+    reinterpret_cast<float4*>(&sm.w2T[0][0])[t] = reinterpret_cast<const float4*>(&Wf->w2T[0][0])[t];
+  }
+  sm.b1[tid] = Wf->b1[tid];
+  if (tid < PF_D) sm.b2[tid] = Wf->b2[tid];
+
+  float wq[4][8];
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const float4 a = reinterpret_cast<const float4*>(Wc->wqk[4 + v])[j];
+    const float4 c = reinterpret_cast<const float4*>(Wc->wqk[4 + v])[8 + j];
+    wq[v][0] = a.x; wq[v][1] = a.y; wq[v][2] = a.z; wq[v][3] = a.w;
+    wq[v][4] = c.x; wq[v][5] = c.y; wq[v][6] = c.z; wq[v][7] = c.w;
+  }
+  const float bq = Wc->bqk[4 + (j >> 1)];
+  float bo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bo[i] = Wc->bo[chan_of(j, i)];
+  __syncthreads();
+
+  const long long n_tiles = (n_tok + FFN32_T - 1) / FFN32_T;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // ---- step 1: column apply, LN (one token per slot) ----
+    const long long tok = tile * FFN32_T + slot;
+    const bool act = tok < n_tok;
+    float x2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x2[i] = 0.f;
+    int l = 0, b = 0;
+    if (act) {
+      l = (int)(tok % L);
+      b = (int)(tok / ((long long)L * Pl));
+      load_tok(x + (size_t)tok * PF_D, j, x2);
+    }
+    {
+      float nv[8];
+      ln_normalize(x2, nv);
+      float pr[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = fmaf(wq[v][i], nv[i], s);
+        pr[v] = s;
+      }
+      const float* cm = colM + ((size_t)b * L + l) * PF_MROW;
+      float mine = phi_elu1(grp_reduce4(pr, j) + bq);
+      mine *= cm[256 + (j >> 1)];
+      float qh[PF_H];
+#pragma unroll
+      for (int h = 0; h < PF_H; ++h) qh[h] = __shfl_sync(PF_FULL, mine, (lane & 24) | (2 * h));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 m = *reinterpret_cast<const float4*>(cm + chan_of(j, i) * 4);
+        float a = bo[i];
+        a = fmaf(m.x, qh[0], a);
+        a = fmaf(m.y, qh[1], a);
+        a = fmaf(m.z, qh[2], a);
+        a = fmaf(m.w, qh[3], a);
+        x2[i] += a;
+      }
+      if (apply_only) {  // test hook: x2 only (uniform branch)
+        if (act) store_tok(x + (size_t)tok * PF_D, j, x2);
+        continue;
+      }
+      ln_normalize(x2, nv);
+      reinterpret_cast<float4*>(sm.A[slot])[j] = make_float4(nv[0], nv[1], nv[2], nv[3]);
+      reinterpret_cast<float4*>(sm.A[slot])[8 + j] = make_float4(nv[4], nv[5], nv[6], nv[7]);
+    }
+    __syncthreads();
+    // ---- step 2: Hid = gelu(A w1T + b1): thread = 4 tokens x 8 hidden units ----
+    {
+      const int ty = tid >> 5, tx = tid & 31;
+      float acc[4][8];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[r][i] = sm.b1[tx + 32 * i];
+#pragma unroll 2
+      for (int k = 0; k < PF_D; k += 4) {
+        float4 a[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a[r] = *reinterpret_cast<const float4*>(&sm.A[4 * ty + r][k]);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          float w[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) w[i] = sm.w1T[k + kk][tx + 32 * i];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const float av = kk == 0 ? a[r].x : kk == 1 ? a[r].y : kk == 2 ? a[r].z : a[r].w;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[r][i] = fmaf(av, w[i], acc[r][i]);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sm.Hid[4 * ty + r][tx + 32 * i] = gelu_erf(acc[r][i]);
+    }
+    __syncthreads();
+    // ---- step 3: O = Hid w2T + b2: thread = 2 tokens x 4 channels; O overwrites A ----
+    {
+      const int ty = tid >> 4, tx = tid & 15;
+      float acc[2][4];
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[r][i] = sm.b2[tx + 16 * i];
+#pragma unroll 2
+      for (int k = 0; k < PF_HID; k += 4) {
+        float4 a[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) a[r] = *reinterpret_cast<const float4*>(&sm.Hid[2 * ty + r][k]);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          float w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) w[i] = sm.w2T[k + kk][tx + 16 * i];
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const float av = kk == 0 ? a[r].x : kk == 1 ? a[r].y : kk == 2 ? a[r].z : a[r].w;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[r][i] = fmaf(av, w[i], acc[r][i]);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sm.A[2 * ty + r][tx + 16 * i] = acc[r][i];
+    }
+    __syncthreads();
+    // ---- step 4: residual, store ----
+    if (act) {
+      const float4 o0 = reinterpret_cast<const float4*>(sm.A[slot])[j];
+      const float4 o1 = reinterpret_cast<const float4*>(sm.A[slot])[8 + j];
+      x2[0] += o0.x; x2[1] += o0.y; x2[2] += o0.z; x2[3] += o0.w;
+      x2[4] += o1.x; x2[5] += o1.y; x2[6] += o1.z; x2[7] += o1.w;
+      store_tok(x + (size_t)tok * PF_D, j, x2);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Distance head: dist[b,p] = mean_l softplus(w . x[b,p,l,:] + c)        model.py:158-164,182-185
+// One CTA per pair-row; fixed-order reduction over the sites.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_head(const PfHeadW* __restrict__ hw, const float* __restrict__ x, int L, float* __restrict__ dist) {
+  __shared__ float red[32];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int j = lane & 7, slot = tid >> 3;
+  const float* xrow = x + (size_t)blockIdx.x * L * PF_D;
+  float w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w[i] = hw->whead[chan_of(j, i)];
+  const float c = hw->bhead;
+  float acc = 0.f;
+  const int n_it = (L + 31) >> 5;
+  for (int it = 0; it < n_it; ++it) {
+    const int l = it * 32 + slot;
+    float xc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xc[i] = 0.f;
+    if (l < L) load_tok(xrow + (size_t)l * PF_D, j, xc);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s = fmaf(w[i], xc[i], s);
+    s = grp_sum(s) + c;
+    if (l < L) acc += softplus20(s);
+  }
+  if (j == 0) red[slot] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s += red[i];
+    dist[blockIdx.x] = s / (float)L;
+  }
+}
+
+// (B,P) upper-triangle vectors -> (B,n,n) symmetric matrices        infer_alns.py:14-25
+__global__ void k_dist_to_matrix(const float* __restrict__ dist, int n, long long P,
+                                 float* __restrict__ mat) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (t >= (long long)n * n) return;
+  const int r = (int)(t / n), c = (int)(t % n);
+  float v = 0.f;
+  if (r != c) {
+    const long long i = r < c ? r : c, jj = r < c ? c : r;
+    v = dist[(size_t)b * P + (i * n - i * (i + 1) / 2 + (jj - i - 1))];
+  }
+  mat[(size_t)b * n * n + t] = v;
+}

@@ -1,0 +1,121 @@
+"""CPU tests of the host side: C-ABI library exports, drop-in module surface, FASTA/PHYLIP
+helpers and pair sharding arithmetic.  No compute call is made (no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from tests._util import GOLDEN, ROOT
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from phyloformer_b200 import _cabi
+    lib = _cabi.load()
+    header = open(os.path.join(ROOT, "include", "pf_sm100.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(pf_[a-z_0-9]+)\s*\(", header)) - {"pf_reduce_fn"}
+    assert declared == set(_cabi.SYMBOLS), declared ^ set(_cabi.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.pf_abi_version() == _cabi.PF_ABI_VERSION
+    m = re.search(r"#define PF_COLSUM_FLOATS (\d+)", header)
+    assert int(m.group(1)) == _cabi.PF_COLSUM_FLOATS == 72
+
+
+def test_bad_arguments_are_rejected_without_a_gpu():
+    from phyloformer_b200 import _cabi
+    lib = _cabi.load()
+    assert lib.pf_workspace_bytes(None, 1, 5, 10, 0, 10) == 0
+    h = ctypes.c_void_p()
+    cfg = _cabi.PfCfg(6, 8, 64, 4, 0)  # 8 heads: not built
+    rc = lib.pf_create(ctypes.byref(h), ctypes.byref(cfg), (ctypes.c_void_p * 160)(), 160)
+    assert rc == -1 and b"nb_heads" in lib.pf_last_error()
+    cfg = _cabi.PfCfg(6, 4, 64, 4, 0)
+    rc = lib.pf_create(ctypes.byref(h), ctypes.byref(cfg), (ctypes.c_void_p * 3)(), 3)
+    assert rc == -1 and b"160" in lib.pf_last_error()
+
+
+def test_module_surface_matches_reference_checkpoint():
+    from phyloformer.model import Phyloformer  # the shim import path used by infer_alns.py
+    from phyloformer_b200.model import weight_names
+    ck = torch.load(os.path.join(GOLDEN, "ckpt_pf.pt"), map_location="cpu")
+    assert ck["hyper_parameters"] == {"nb_blocks": 6, "nb_heads": 4, "embed_dim": 64, "dropout": 0.0}
+    params = dict(ck["hyper_parameters"]); params["device"] = "cpu"
+    m = Phyloformer(**params)
+    sd = {k.replace("model.", ""): v for k, v in ck["state_dict"].items() if k != "model.seq2pair"}
+    res = m.load_state_dict(sd, strict=False)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert list(m.state_dict().keys()) == list(sd.keys())           # same keys, same order
+    assert sorted(weight_names(6)) == sorted(sd.keys())
+    for k, v in m.state_dict().items():
+        assert v.shape == sd[k].shape and torch.equal(v, sd[k])
+    m.eval()
+    # reference-style constructor spellings
+    assert Phyloformer(n_blocks=2).nb_blocks == 2
+    with pytest.raises(ValueError):
+        Phyloformer(n_heads=8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 22, 7, 4))
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 21, 7, 4))
+
+
+def test_load_alignment_matches_reference_tensor():
+    from phyloformer.data import load_alignment, load_alignment_idx
+    g = np.load(os.path.join(GOLDEN, "ref_load_alignment.npz"))
+    aln, ids = load_alignment(os.path.join(GOLDEN, "msas", "0_20_tips.fa"))
+    assert aln.dtype == torch.int64 and tuple(aln.shape) == g["aln"].shape
+    assert np.array_equal(aln.numpy().astype(np.int8), g["aln"]) and ids == list(g["ids"])
+    idx, _ = load_alignment_idx(os.path.join(GOLDEN, "msas", "0_20_tips.fa"))
+    assert idx.dtype == torch.uint8 and tuple(idx.shape) == (20, 250)
+
+
+def test_load_alignment_errors(tmp_path):
+    from phyloformer.data import load_alignment_idx
+    p = tmp_path / "bad.fa"
+    p.write_text(">a\nACDZ\n>b\nACDE\n")          # Z is not in ALPHABET
+    with pytest.raises(KeyError):
+        load_alignment_idx(str(p))
+    p.write_text(">a\nACD\n>b\nACDE\n")
+    with pytest.raises(ValueError):
+        load_alignment_idx(str(p))
+    p.write_text(">a\nAC\nDE\n>b\nAC-X\n")         # multi-line records, gap and X
+    idx, ids = load_alignment_idx(str(p))
+    assert ids == ["a", "b"] and idx.tolist() == [[0, 4, 3, 6], [0, 4, 21, 20]]
+
+
+def test_phylip_text_matches_reference(ref_testdata):
+    import infer_alns
+    from phyloformer.data import load_alignment_idx
+    for stem in ("0_20_tips", "3_50_tips"):
+        _, ids = load_alignment_idx(os.path.join(GOLDEN, "msas", stem + ".fa"))
+        _, txt = infer_alns.vec_to_phylip(torch.from_numpy(ref_testdata[stem]), ids)
+        assert txt == open(os.path.join(GOLDEN, f"ref_phylip_{stem}.phy")).read()
+
+
+def test_cli_requires_cuda(tmp_path):
+    import infer_alns
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        infer_alns.main([os.path.join(GOLDEN, "ckpt_pf.pt"), os.path.join(GOLDEN, "msas"), "-o", str(tmp_path)])
+
+
+def test_pair_sharding_arithmetic():
+    from phyloformer_b200 import sharding as sh
+    for n in (2, 3, 7, 50, 200, 501):
+        P = sh.n_pairs(n)
+        ij = torch.triu_indices(n, n, 1)
+        for p in {0, 1, P // 3, P // 2, P - 2, P - 1} & set(range(P)):
+            i, j = sh.pair_to_ij(p, n)
+            assert (i, j) == (int(ij[0, p]), int(ij[1, p])) and sh.pair_index(i, j, n) == p
+        for world in (1, 2, 3, 8):
+            r = sh.all_ranges(n, world)
+            assert r[0][0] == 0 and r[-1][1] == P
+            assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+            sizes = [hi - lo for lo, hi in r]
+            assert max(sizes) - min(sizes) <= 1
+    assert sh.batch_range(256, 3, 8) == (96, 128)
