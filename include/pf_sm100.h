@@ -114,6 +114,14 @@ int pf_dist_to_matrix(const float* dist_dev, int B, int n, float* mat_dev, void*
  * gpu_launches claim). */
 int pf_last_launch_count(pf_handle h);
 
+/* Synchronises and returns PF_ERR_CUDA if a kernel raised the device-side error flag (a
+ * tensor-core pipeline wait that timed out instead of hanging the GPU); clears the flag. */
+int pf_device_error(pf_handle h);
+
+/* Test hook: when non-NULL, the tcgen05 FFN kernel copies the raw fp32 accumulators of its
+ * first 128-token tile to dump_dev as [128][320] (columns 0..255 = GEMM1, 256..319 = GEMM2). */
+int pf_debug_set_dump(pf_handle h, float* dump_dev);
+
 /* Per-kernel device timing (bench.py's roofline leg): when enabled, pf_forward brackets every
  * kernel launch with CUDA events on `stream`.  pf_profile_read waits for them and returns, per
  * kernel class, the summed milliseconds and the number of launches since the last read. */

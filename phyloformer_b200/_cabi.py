@@ -39,6 +39,8 @@ SYMBOLS = {
                                  c_void_p, c_void_p, c_size_t, c_void_p, REDUCE_FN, c_void_p, c_int, c_void_p]),
     "pf_dist_to_matrix": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "pf_last_launch_count": (c_int, [c_void_p]),
+    "pf_device_error": (c_int, [c_void_p]),
+    "pf_debug_set_dump": (c_int, [c_void_p, c_void_p]),
     "pf_profile_enable": (c_int, [c_void_p, c_int]),
     "pf_profile_read": (c_int, [c_void_p, POINTER(c_float), POINTER(c_int32)]),
 }

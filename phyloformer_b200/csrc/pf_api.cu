@@ -52,6 +52,8 @@ struct pf_ctx {
   PfBlockW* blk_dev = nullptr;  // [nb]
   PfFfnTcW* tc_dev = nullptr;   // [nb] bf16 hi/lo smem images for the tcgen05 FFN
   int launches = 0;
+  int* err_dev = nullptr;       // set by a kernel whose mbarrier wait timed out
+  float* dump_dev = nullptr;    // test hook: raw accumulators of the first FFN tile
   // optional per-kernel timing (pf_profile_*)
   bool prof = false;
   struct Rec { int kc; cudaEvent_t a, b; };
@@ -231,6 +233,8 @@ int pf_create(pf_handle* out, const pf_cfg* cfg, const float* const* weights_dev
   if ((e = cudaMalloc(&h->head_dev, sizeof(PfHeadW))) != cudaSuccess ||
       (e = cudaMalloc(&h->blk_dev, sizeof(PfBlockW) * nb)) != cudaSuccess ||
       (e = cudaMalloc(&h->tc_dev, sizeof(PfFfnTcW) * nb)) != cudaSuccess ||
+      (e = cudaMalloc(&h->err_dev, sizeof(int))) != cudaSuccess ||
+      (e = cudaMemset(h->err_dev, 0, sizeof(int))) != cudaSuccess ||
       (e = cudaMemcpy(h->head_dev, head.data(), sizeof(PfHeadW), cudaMemcpyHostToDevice)) != cudaSuccess ||
       (e = cudaMemcpy(h->blk_dev, blk.data(), sizeof(PfBlockW) * nb, cudaMemcpyHostToDevice)) != cudaSuccess ||
       (e = cudaMemcpy(h->tc_dev, tc.data(), sizeof(PfFfnTcW) * nb, cudaMemcpyHostToDevice)) != cudaSuccess) {
@@ -253,6 +257,7 @@ void pf_destroy(pf_handle h) {
   if (h->head_dev) cudaFree(h->head_dev);
   if (h->blk_dev) cudaFree(h->blk_dev);
   if (h->tc_dev) cudaFree(h->tc_dev);
+  if (h->err_dev) cudaFree(h->err_dev);
   for (auto& r : h->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : h->pool) cudaEventDestroy(e);
   delete h;
@@ -384,7 +389,7 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
     } else {
       Timed t_(h, PF_KC_FFN, st);
       const int rc = pf_ffn_tc_launch(&bw->col, h->tc_dev + b, x, colM, L, (int)pl.Pl, n_tok, h->n_sm,
-                                      h->cfg.precision == PF_PREC_BF16 ? 1 : 3, st);
+                                      h->cfg.precision == PF_PREC_BF16 ? 1 : 3, h->err_dev, h->dump_dev, st);
       if (rc != 0) return fail(PF_ERR_CUDA, "pf_forward: tcgen05 FFN launch failed (%d)", rc);
     }
     CUDA_TRY(cudaGetLastError());
@@ -418,6 +423,23 @@ int pf_dist_to_matrix(const float* dist_dev, int B, int n, float* mat_dev, void*
 }
 
 int pf_last_launch_count(pf_handle h) { return h ? h->launches : 0; }
+
+int pf_device_error(pf_handle h) {
+  if (!h) return fail(PF_ERR_ARG, "pf_device_error: null handle");
+  int v = 0;
+  CUDA_TRY(cudaMemcpy(&v, h->err_dev, sizeof(int), cudaMemcpyDeviceToHost));
+  if (v != 0) {
+    cudaMemset(h->err_dev, 0, sizeof(int));
+    return fail(PF_ERR_CUDA, "a tensor-core pipeline barrier timed out on the device (flag %d)", v);
+  }
+  return PF_OK;
+}
+
+int pf_debug_set_dump(pf_handle h, float* dump_dev) {
+  if (!h) return fail(PF_ERR_ARG, "pf_debug_set_dump: null handle");
+  h->dump_dev = dump_dev;
+  return PF_OK;
+}
 
 int pf_profile_enable(pf_handle h, int on) {
   if (!h) return fail(PF_ERR_ARG, "pf_profile_enable: null handle");

@@ -1,14 +1,433 @@
-// pf_ffn_tc.cuh -- tcgen05/TMEM implementation of column-apply + FFN (placeholder: filled in
-// by the next milestone; the fp32 FFMA kernel in pf_kernels.cuh is the path until then).
+// pf_ffn_tc.cuh -- column apply + LayerNorm + FFN + residual on the 5th-gen tensor cores.
+//
+//   x2 = x1 + M_l qhat + bo ;  x3 = x2 + W2 gelu(W1 LN(x2) + b1) + b2       (model.py:97-104)
+//
+// The FFN (64 -> 256 -> 64 per token) is the only dense contraction on the path.  It runs as
+// two tcgen05.mma GEMMs per 128-token tile with fp32 accumulators in TMEM:
+//   GEMM1  D1[128x256] = A1[128x64]  . W1^T      A1 = LN(x2) from shared memory   (SS form)
+//   GEMM2  D2[128x64]  = H [128x256] . W2^T      H  = gelu(D1 + b1) from TMEM     (TS form)
+// Parity mode ("bf16x3") splits every fp32 operand into bf16 hi + lo and issues the three
+// products hi.hi + hi.lo + lo.hi (9e-5 max-rel end to end); fast mode
+// ("bf16") issues hi.hi only.
+//
+// Data movement: both weight matrices (hi and lo, 128 KB) are staged once per CTA into
+// shared memory as pre-swizzled (SWIZZLE_128B, K-major) UMMA images built on the host; the
+// kernel is persistent (one CTA per SM) so they are read from L2 once per SM.  The hidden
+// activations never leave the SM: the epilogue of GEMM1 rewrites D1's TMEM columns in place
+// with packed bf16 hi/lo pairs, which GEMM2 consumes as its A operand straight from TMEM.
+// HBM traffic is one fp32 read and one fp32 write of the token (512 B).
 #pragma once
+#include <cuda_bf16.h>
+
 #include "pf_common.cuh"
 
+#define TC_TILE 128
+#define TC_THREADS 256
+
 struct PfFfnTcW {
-  float pad[4];
+  // UMMA K-major SWIZZLE_128B images (see umma_off_*): bf16 bit patterns
+  uint16_t w1hi[PF_HID * PF_D];  // B of GEMM1: [n = hidden 256][k = 64]
+  uint16_t w1lo[PF_HID * PF_D];
+  uint16_t w2hi[PF_D * PF_HID];  // B of GEMM2: [n = out 64][k = hidden 256], 4 K-atoms of 64
+  uint16_t w2lo[PF_D * PF_HID];
+  float b1[PF_HID];
+  float b2[PF_D];
 };
-inline void pf_pack_ffn_tc(const PfFfnW&, PfFfnTcW*) {}
-inline int pf_ffn_tc_init() { return 0; }
-inline int pf_ffn_tc_launch(const PfAttnW*, const PfFfnTcW*, float*, const float*, int, int, long long, int, int,
-                            cudaStream_t) {
-  return -1;
+
+// Byte offset of element (row, k) in a K-major SWIZZLE_128B operand whose K extent is 64
+// (one 128-byte swizzle atom per row): 8-row groups of 1024 B, 16-byte chunk index XORed with
+// the row index inside the group (Swizzle<3,4,3>).
+__host__ __device__ inline uint32_t umma_off_k64(int row, int k) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ row) & 7) << 4) + (k & 7) * 2);
+}
+// Same for K = 256 with `rows` rows: four K-atoms, each a (rows x 128 B) block.
+__host__ __device__ inline uint32_t umma_off_k256(int row, int k, int rows) {
+  return (uint32_t)((k >> 6) * rows * 128) + umma_off_k64(row, k & 63);
+}
+
+inline uint16_t f32_to_bf16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+inline float bf16_to_f32(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+inline void pf_pack_ffn_tc(const PfFfnW& f, PfFfnTcW* o) {
+  for (int n = 0; n < PF_HID; ++n)
+    for (int k = 0; k < PF_D; ++k) {
+      const float w = f.w1T[k][n];
+      const uint16_t hi = f32_to_bf16_rn(w);
+      const uint16_t lo = f32_to_bf16_rn(w - bf16_to_f32(hi));
+      const uint32_t off = umma_off_k64(n, k) / 2;
+      o->w1hi[off] = hi;
+      o->w1lo[off] = lo;
+    }
+  for (int n = 0; n < PF_D; ++n)
+    for (int k = 0; k < PF_HID; ++k) {
+      const float w = f.w2T[k][n];
+      const uint16_t hi = f32_to_bf16_rn(w);
+      const uint16_t lo = f32_to_bf16_rn(w - bf16_to_f32(hi));
+      const uint32_t off = umma_off_k256(n, k, PF_D) / 2;
+      o->w2hi[off] = hi;
+      o->w2lo[off] = lo;
+    }
+  memcpy(o->b1, f.b1, sizeof(o->b1));
+  memcpy(o->b2, f.b2, sizeof(o->b2));
+}
+
+// ---- shared memory carve-up (offsets from a 1024-byte aligned base) -------------------------
+#define TC_OFF_W1HI 0
+#define TC_OFF_W1LO 32768
+#define TC_OFF_W2HI 65536
+#define TC_OFF_W2LO 98304
+#define TC_OFF_A1HI 131072
+#define TC_OFF_A1LO 147456
+#define TC_OFF_XS 163840   // [128][64] fp32 residual / output staging, chunk-swizzled
+#define TC_OFF_B1 196608
+#define TC_OFF_B2 197632
+#define TC_OFF_BAR 197888  // 2 mbarriers
+#define TC_OFF_TMEM 197904
+#define TC_SMEM_BYTES (197920 + 1024)
+#define TC_TMEM_COLS 512
+#define TC_COL_D2 256
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+// Bounded wait: returns false if the barrier did not complete (the caller raises an error flag
+// instead of hanging the GPU).
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 1000;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor: start>>4 | LBO(unused)=1 | SBO=1024>>4 |
+// version=1 (bit 46) | layout_type=SWIZZLE_128B (2 at bits 61..63)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// kind::f16 instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), K-major A and B,
+// N>>3 at bit 17, M>>4 at bit 24.
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+// position (in float4 chunks) of logical chunk c of row r in the XS staging buffer
+__device__ __forceinline__ int xs_chunk(int r, int c) { return (c & 8) | ((c ^ r) & 7); }
+
+// n_terms: 3 = bf16x3 (hi.hi + hi.lo + lo.hi), 1 = bf16 (hi.hi)
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_colapply_ffn_tc(const PfAttnW* __restrict__ Wc, const PfFfnTcW* __restrict__ Wt, float* __restrict__ x,
+                  const float* __restrict__ colM, int L, int Pl, long long n_tok, int n_terms,
+                  int* __restrict__ err_flag, float* __restrict__ dump) {
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(sm);
+  float* XS = reinterpret_cast<float*>(sm + TC_OFF_XS);
+  float* sb1 = reinterpret_cast<float*>(sm + TC_OFF_B1);
+  float* sb2 = reinterpret_cast<float*>(sm + TC_OFF_B2);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + TC_OFF_TMEM);
+  const uint32_t bar1 = sbase + TC_OFF_BAR, bar2 = sbase + TC_OFF_BAR + 8;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j = lane & 7, slot = tid >> 3;
+
+  // ---- one-time setup: weights -> smem, barriers, TMEM ----
+  {
+    const int4* src = reinterpret_cast<const int4*>(Wt->w1hi);  // w1hi,w1lo,w2hi,w2lo are contiguous
+    int4* dst = reinterpret_cast<int4*>(sm + TC_OFF_W1HI);
+    for (int i = tid; i < 131072 / 16; i += TC_THREADS) dst[i] = src[i];
+    sb1[tid] = Wt->b1[tid];
+    if (tid < PF_D) sb2[tid] = Wt->b2[tid];
+  }
+  if (tid == 0) {
+    mbar_init(bar1, 1);
+    mbar_init(bar2, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + TC_OFF_TMEM), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // column-attention q weights for this lane's channels (same mapping as the fp32 kernel)
+  float wq[4][8];
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const float4 a = reinterpret_cast<const float4*>(Wc->wqk[4 + v])[j];
+    const float4 c = reinterpret_cast<const float4*>(Wc->wqk[4 + v])[8 + j];
+    wq[v][0] = a.x; wq[v][1] = a.y; wq[v][2] = a.z; wq[v][3] = a.w;
+    wq[v][4] = c.x; wq[v][5] = c.y; wq[v][6] = c.z; wq[v][7] = c.w;
+  }
+  const float bq = Wc->bqk[4 + (j >> 1)];
+  float bo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bo[i] = Wc->bo[chan_of(j, i)];
+
+  const uint32_t idesc1 = umma_idesc(128, 256), idesc2 = umma_idesc(128, 64);
+  const long long n_tiles = (n_tok + TC_TILE - 1) / TC_TILE;
+  uint32_t phase = 0;
+  bool ok = true;
+
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // ================= prologue: column apply, LN, bf16 hi/lo split -> A1 =================
+#pragma unroll 1
+    for (int pass = 0; pass < TC_TILE / 32; ++pass) {
+      const int r = pass * 32 + slot;
+      const long long tok = tile * TC_TILE + r;
+      const bool act = tok < n_tok;
+      float x2[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x2[i] = 0.f;
+      int l = 0, b = 0;
+      if (act) {
+        l = (int)(tok % L);
+        b = (int)(tok / ((long long)L * Pl));
+        load_tok(x + (size_t)tok * PF_D, j, x2);
+      }
+      float nv[8];
+      ln_normalize(x2, nv);
+      float pr[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = fmaf(wq[v][i], nv[i], s);
+        pr[v] = s;
+      }
+      const float* cm = colM + ((size_t)b * L + l) * PF_MROW;
+      float mine = phi_elu1(grp_reduce4(pr, j) + bq);
+      mine *= cm[256 + (j >> 1)];
+      float qh[PF_H];
+#pragma unroll
+      for (int h = 0; h < PF_H; ++h) qh[h] = __shfl_sync(PF_FULL, mine, (lane & 24) | (2 * h));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 m = *reinterpret_cast<const float4*>(cm + chan_of(j, i) * 4);
+        float a = bo[i];
+        a = fmaf(m.x, qh[0], a);
+        a = fmaf(m.y, qh[1], a);
+        a = fmaf(m.z, qh[2], a);
+        a = fmaf(m.w, qh[3], a);
+        x2[i] += a;
+      }
+      // residual copy (fp32) for the epilogue
+      float4* xr = reinterpret_cast<float4*>(XS + r * PF_D);
+      xr[xs_chunk(r, j)] = make_float4(x2[0], x2[1], x2[2], x2[3]);
+      xr[xs_chunk(r, 8 + j)] = make_float4(x2[4], x2[5], x2[6], x2[7]);
+      ln_normalize(x2, nv);
+      // hi/lo split; channels 4j..4j+3 -> 16B chunk j>>1 (half j&1); 32+4j.. -> chunk 4+(j>>1)
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(nv[2 * i], nv[2 * i + 1]);
+        const __nv_bfloat162 ll = __floats2bfloat162_rn(nv[2 * i] - __low2float(hh), nv[2 * i + 1] - __high2float(hh));
+        hi[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        lo[i] = *reinterpret_cast<const uint32_t*>(&ll);
+      }
+      const uint32_t rowoff = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+      const uint32_t o0 = rowoff + ((((j >> 1)) ^ (r & 7)) << 4) + (j & 1) * 8;
+      const uint32_t o1 = rowoff + (((4 + (j >> 1)) ^ (r & 7)) << 4) + (j & 1) * 8;
+      *reinterpret_cast<uint2*>(sm + TC_OFF_A1HI + o0) = make_uint2(hi[0], hi[1]);
+      *reinterpret_cast<uint2*>(sm + TC_OFF_A1HI + o1) = make_uint2(hi[2], hi[3]);
+      *reinterpret_cast<uint2*>(sm + TC_OFF_A1LO + o0) = make_uint2(lo[0], lo[1]);
+      *reinterpret_cast<uint2*>(sm + TC_OFF_A1LO + o1) = make_uint2(lo[2], lo[3]);
+    }
+    fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    // ================= GEMM1: D1 = A1 . W1^T  (SS, N=256, K=64 in 4 steps) =================
+    if (tid == 0) {
+      tc_fence_after();
+      uint32_t acc = 0;
+      for (int t = 0; t < n_terms; ++t) {
+        const uint32_t a_base = sbase + ((t == 2) ? TC_OFF_A1LO : TC_OFF_A1HI);
+        const uint32_t b_base = sbase + ((t == 1) ? TC_OFF_W1LO : TC_OFF_W1HI);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          umma_ss(tmem, umma_desc(a_base + s * 32), umma_desc(b_base + s * 32), idesc1, acc);
+          acc = 1;
+        }
+      }
+      tc_commit(bar1);
+    }
+    ok = mbar_wait(bar1, phase) && ok;
+    tc_fence_after();
+    // ================= epilogue 1: H = gelu(D1 + b1), bf16 hi/lo, in place in TMEM ==========
+    {
+      const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+      const int col0 = (warp >> 2) * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int cc = col0 + c * 32;
+        uint32_t v[32];
+        tmem_ld32(tmem + lane_base + cc, v);
+        tc_wait_ld();
+        if (dump != nullptr && blockIdx.x == 0 && tile == blockIdx.x) {
+          const int row = (warp & 3) * 32 + lane;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) dump[row * 320 + cc + i] = __uint_as_float(v[i]);
+        }
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float g0 = gelu_erf(__uint_as_float(v[2 * i]) + sb1[cc + 2 * i]);
+          const float g1 = gelu_erf(__uint_as_float(v[2 * i + 1]) + sb1[cc + 2 * i + 1]);
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(g0, g1);
+          const __nv_bfloat162 ll = __floats2bfloat162_rn(g0 - __low2float(hh), g1 - __high2float(hh));
+          hi[i] = *reinterpret_cast<const uint32_t*>(&hh);
+          lo[i] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        tmem_st16(tmem + lane_base + cc, hi);
+        tmem_st16(tmem + lane_base + cc + 16, lo);
+      }
+      tc_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    // ================= GEMM2: D2 = H . W2^T  (TS, N=64, K=256 in 16 steps) ==================
+    if (tid == 0) {
+      tc_fence_after();
+      uint32_t acc = 0;
+      for (int t = 0; t < n_terms; ++t) {
+        const uint32_t b_base = sbase + ((t == 2) ? TC_OFF_W2LO : TC_OFF_W2HI);
+        const uint32_t a_sel = (t == 1) ? 16u : 0u;  // t=1: H_lo . W2_hi
+#pragma unroll
+        for (int s = 0; s < 16; ++s) {
+          const uint32_t a_col = (uint32_t)(32 * (s >> 1) + 8 * (s & 1)) + a_sel;
+          const uint32_t b_off = (uint32_t)((s >> 2) * (PF_D * 128) + (s & 3) * 32);
+          umma_ts(tmem + TC_COL_D2, tmem + a_col, umma_desc(b_base + b_off), idesc2, acc);
+          acc = 1;
+        }
+      }
+      tc_commit(bar2);
+    }
+    ok = mbar_wait(bar2, phase) && ok;
+    tc_fence_after();
+    phase ^= 1;
+    // ================= epilogue 2: y = x2 + D2 + b2 -> XS ==================================
+    {
+      const int r = (warp & 3) * 32 + lane;
+      const int hf = warp >> 2;
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + TC_COL_D2 + hf * 32, v);
+      tc_wait_ld();
+      if (dump != nullptr && blockIdx.x == 0 && tile == blockIdx.x) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) dump[r * 320 + 256 + hf * 32 + i] = __uint_as_float(v[i]);
+      }
+      float4* xr = reinterpret_cast<float4*>(XS + r * PF_D);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = hf * 8 + i;
+        float4 t = xr[xs_chunk(r, c)];
+        t.x += __uint_as_float(v[4 * i + 0]) + sb2[4 * c + 0];
+        t.y += __uint_as_float(v[4 * i + 1]) + sb2[4 * c + 1];
+        t.z += __uint_as_float(v[4 * i + 2]) + sb2[4 * c + 2];
+        t.w += __uint_as_float(v[4 * i + 3]) + sb2[4 * c + 3];
+        xr[xs_chunk(r, c)] = t;
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    // ================= store: coalesced fp32 rows back to HBM ===============================
+#pragma unroll 1
+    for (int pass = 0; pass < TC_TILE / 32; ++pass) {
+      const int r = pass * 32 + slot;
+      const long long tok = tile * TC_TILE + r;
+      if (tok < n_tok) {
+        const float4* xr = reinterpret_cast<const float4*>(XS + r * PF_D);
+        float4* g = reinterpret_cast<float4*>(x + (size_t)tok * PF_D);
+        g[j] = xr[xs_chunk(r, j)];
+        g[8 + j] = xr[xs_chunk(r, 8 + j)];
+      }
+    }
+    __syncthreads();
+  }
+  if (!ok && err_flag != nullptr) *err_flag = 1;
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+inline int pf_ffn_tc_init() {
+  return (int)cudaFuncSetAttribute(k_colapply_ffn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+}
+
+inline int pf_ffn_tc_launch(const PfAttnW* Wc, const PfFfnTcW* Wt, float* x, const float* colM, int L, int Pl,
+                            long long n_tok, int n_sm, int n_terms, int* err_flag, float* dump, cudaStream_t st) {
+  const long long tiles = (n_tok + TC_TILE - 1) / TC_TILE;
+  const int grid = (int)(tiles < n_sm ? tiles : n_sm);
+  k_colapply_ffn_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(Wc, Wt, x, colM, L, Pl, n_tok, n_terms, err_flag, dump);
+  return (int)cudaGetLastError();
 }

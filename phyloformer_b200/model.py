@@ -311,6 +311,26 @@ class Phyloformer(nn.Module):
             _cabi.check(lib.pf_dist_to_matrix(d2.data_ptr(), B, n, mat.data_ptr(), stream), "pf_dist_to_matrix")
         return mat
 
+    def debug_tc_dump(self, idx: torch.Tensor):
+        """Test hook: run one forward and return the raw tcgen05 accumulators of the first
+        128-token tile of the LAST block's FFN kernel as a (128, 320) tensor."""
+        lib = _cabi.load()
+        idx = idx[None] if idx.dim() == 2 else idx
+        self.forward_idx(idx)  # make sure the handle exists
+        dump = torch.zeros((128, 320), dtype=torch.float32, device=idx.device)
+        _cabi.check(lib.pf_debug_set_dump(self._handle, dump.data_ptr()), "pf_debug_set_dump")
+        try:
+            self.forward_idx(idx)
+            torch.cuda.synchronize(idx.device)
+        finally:
+            _cabi.check(lib.pf_debug_set_dump(self._handle, None), "pf_debug_set_dump")
+        return dump
+
+    def check_device_error(self):
+        """Synchronise and raise if a kernel reported a device-side pipeline timeout."""
+        if self._handle is not None:
+            _cabi.check(_cabi.load().pf_device_error(self._handle), "device check")
+
     def profile_enable(self, on: bool = True):
         """Bracket every kernel of the following forwards with CUDA events (bench.py)."""
         if self._handle is None:
