@@ -22,7 +22,7 @@
 #include "pf_common.cuh"
 
 #define TC_TILE 128
-#define TC_THREADS 256
+#define TC_THREADS 512
 
 struct PfFfnTcW {
   // UMMA K-major SWIZZLE_128B images (see umma_off_*): bf16 bit patterns
@@ -89,12 +89,12 @@ inline void pf_pack_ffn_tc(const PfFfnW& f, PfFfnTcW* o) {
 #define TC_OFF_W2LO 98304
 #define TC_OFF_A1HI 131072
 #define TC_OFF_A1LO 147456
-#define TC_OFF_XS 163840   // [128][64] fp32 residual / output staging, chunk-swizzled
-#define TC_OFF_B1 196608
-#define TC_OFF_B2 197632
-#define TC_OFF_BAR 197888  // 2 mbarriers
-#define TC_OFF_TMEM 197904
-#define TC_SMEM_BYTES (197920 + 1024)
+#define TC_OFF_XS 163840   // 2 x [128][64] fp32 residual / output staging, chunk-swizzled
+#define TC_OFF_B1 229376
+#define TC_OFF_B2 230400
+#define TC_OFF_BAR 230656  // 2 mbarriers
+#define TC_OFF_TMEM 230672
+#define TC_SMEM_BYTES (230720 + 1024)
 #define TC_TMEM_COLS 512
 #define TC_COL_D2 256
 
@@ -174,10 +174,53 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+// GELU(h) = max(h,0) - |h| * 0.5 erfc(|h|/sqrt2), with 0.5 erfc(z) ~ 1/(c p(z))^16 (Abramowitz &
+// Stegun 7.1.28, the 0.5 and the 1/sqrt2 folded into the coefficients).  fp32 evaluation:
+// max abs error 9.5e-7, rms 2e-7 over [-12,12] (tools/gelu_fit.py) -- an order of magnitude
+// below the bf16x3 product error it feeds.  13 FMA-pipe + 1 ALU + 1 MUFU per element.
+__device__ __forceinline__ float gelu_fast(float h) {
+  const float t = fabsf(h);
+  float p = 5.6212996640e-06f;
+  p = fmaf(p, t, 5.1055209009e-05f);
+  p = fmaf(p, t, 3.9686137011e-05f);
+  p = fmaf(p, t, 3.4227392389e-03f);
+  p = fmaf(p, t, 2.2076998457e-02f);
+  p = fmaf(p, t, 5.2075163037e-02f);
+  p = fmaf(p, t, 1.0442737824e+00f);
+  p *= p; p *= p; p *= p; p *= p;
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
+  return fmaxf(h, 0.f) - fabsf(h * r);
+}
+#ifdef PF_TC_EXACT_GELU
+#define TC_GELU gelu_erf
+#else
+#define TC_GELU gelu_fast
+#endif
+
 // position (in float4 chunks) of logical chunk c of row r in the XS staging buffer
 __device__ __forceinline__ int xs_chunk(int r, int c) { return (c & 8) | ((c ^ r) & 7); }
 
 // n_terms: 3 = bf16x3 (hi.hi + hi.lo + lo.hi), 1 = bf16 (hi.hi)
+//
+// Software pipeline (all 16 warps share every role; one elected thread issues the MMAs):
+//   E1(i) -> issue G2(i) -> P(i+1) [hides G2(i)] -> issue G1(i+1) -> E2(i), store(i) [hide G1(i+1)]
+// P = prologue (column apply, LN, split -> A1 smem), G1/G2 = the two tcgen05 GEMMs,
+// E1 = GELU epilogue in TMEM, E2 = residual epilogue through the XS staging buffer.
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_colapply_ffn_tc(const PfAttnW* __restrict__ Wc, const PfFfnTcW* __restrict__ Wt, float* __restrict__ x,
                   const float* __restrict__ colM, int L, int Pl, long long n_tok, int n_terms,
@@ -185,21 +228,20 @@ k_colapply_ffn_tc(const PfAttnW* __restrict__ Wc, const PfFfnTcW* __restrict__ W
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(sm);
-  float* XS = reinterpret_cast<float*>(sm + TC_OFF_XS);
   float* sb1 = reinterpret_cast<float*>(sm + TC_OFF_B1);
   float* sb2 = reinterpret_cast<float*>(sm + TC_OFF_B2);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + TC_OFF_TMEM);
   const uint32_t bar1 = sbase + TC_OFF_BAR, bar2 = sbase + TC_OFF_BAR + 8;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int j = lane & 7, slot = tid >> 3;
+  const int j = lane & 7, slot = tid >> 3;  // 64 token slots
 
   // ---- one-time setup: weights -> smem, barriers, TMEM ----
   {
     const int4* src = reinterpret_cast<const int4*>(Wt->w1hi);  // w1hi,w1lo,w2hi,w2lo are contiguous
     int4* dst = reinterpret_cast<int4*>(sm + TC_OFF_W1HI);
     for (int i = tid; i < 131072 / 16; i += TC_THREADS) dst[i] = src[i];
-    sb1[tid] = Wt->b1[tid];
+    if (tid < PF_HID) sb1[tid] = Wt->b1[tid];
     if (tid < PF_D) sb2[tid] = Wt->b2[tid];
   }
   if (tid == 0) {
@@ -227,20 +269,19 @@ k_colapply_ffn_tc(const PfAttnW* __restrict__ Wc, const PfFfnTcW* __restrict__ W
     wq[v][4] = c.x; wq[v][5] = c.y; wq[v][6] = c.z; wq[v][7] = c.w;
   }
   const float bq = Wc->bqk[4 + (j >> 1)];
-  float bo[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) bo[i] = Wc->bo[chan_of(j, i)];
 
   const uint32_t idesc1 = umma_idesc(128, 256), idesc2 = umma_idesc(128, 64);
   const long long n_tiles = (n_tok + TC_TILE - 1) / TC_TILE;
-  uint32_t phase = 0;
-  bool ok = true;
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  const int row_t = (warp & 3) * 32 + lane;  // this thread's row in the TMEM epilogues
+  const int cgrp = warp >> 2;                // this warp's column group (0..3)
 
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    // ================= prologue: column apply, LN, bf16 hi/lo split -> A1 =================
+  // ---- prologue: column apply, LN, bf16 hi/lo split -> A1 (UMMA layout), x2 -> XS[buf] ----
+  auto prologue = [&](long long tile, int buf) {
+    float* XS = reinterpret_cast<float*>(sm + TC_OFF_XS + buf * 32768);
 #pragma unroll 1
-    for (int pass = 0; pass < TC_TILE / 32; ++pass) {
-      const int r = pass * 32 + slot;
+    for (int pass = 0; pass < TC_TILE / 64; ++pass) {
+      const int r = pass * 64 + slot;
       const long long tok = tile * TC_TILE + r;
       const bool act = tok < n_tok;
       float x2[8];
@@ -270,20 +311,20 @@ k_colapply_ffn_tc(const PfAttnW* __restrict__ Wc, const PfFfnTcW* __restrict__ W
       for (int h = 0; h < PF_H; ++h) qh[h] = __shfl_sync(PF_FULL, mine, (lane & 24) | (2 * h));
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float4 m = *reinterpret_cast<const float4*>(cm + chan_of(j, i) * 4);
-        float a = bo[i];
+        const int c = chan_of(j, i);
+        const float4 m = *reinterpret_cast<const float4*>(cm + c * 4);
+        float a = Wc->bo[c];
         a = fmaf(m.x, qh[0], a);
         a = fmaf(m.y, qh[1], a);
         a = fmaf(m.z, qh[2], a);
         a = fmaf(m.w, qh[3], a);
         x2[i] += a;
       }
-      // residual copy (fp32) for the epilogue
       float4* xr = reinterpret_cast<float4*>(XS + r * PF_D);
       xr[xs_chunk(r, j)] = make_float4(x2[0], x2[1], x2[2], x2[3]);
       xr[xs_chunk(r, 8 + j)] = make_float4(x2[4], x2[5], x2[6], x2[7]);
       ln_normalize(x2, nv);
-      // hi/lo split; channels 4j..4j+3 -> 16B chunk j>>1 (half j&1); 32+4j.. -> chunk 4+(j>>1)
+      // channels 4j..4j+3 -> 16B chunk j>>1 (half j&1); 32+4j.. -> chunk 4+(j>>1)
       uint32_t hi[4], lo[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -300,107 +341,123 @@ k_colapply_ffn_tc(const PfAttnW* __restrict__ Wc, const PfFfnTcW* __restrict__ W
       *reinterpret_cast<uint2*>(sm + TC_OFF_A1LO + o0) = make_uint2(lo[0], lo[1]);
       *reinterpret_cast<uint2*>(sm + TC_OFF_A1LO + o1) = make_uint2(lo[2], lo[3]);
     }
-    fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-    tc_fence_before();
-    __syncthreads();
-    // ================= GEMM1: D1 = A1 . W1^T  (SS, N=256, K=64 in 4 steps) =================
-    if (tid == 0) {
-      tc_fence_after();
-      uint32_t acc = 0;
-      for (int t = 0; t < n_terms; ++t) {
-        const uint32_t a_base = sbase + ((t == 2) ? TC_OFF_A1LO : TC_OFF_A1HI);
-        const uint32_t b_base = sbase + ((t == 1) ? TC_OFF_W1LO : TC_OFF_W1HI);
+  };
+  // ---- GEMM1: D1 = A1 . W1^T  (SS, N=256, K=64 in 4 steps), one thread ----
+  auto issue_g1 = [&]() {
+    tc_fence_after();
+    uint32_t acc = 0;
+    for (int t = 0; t < n_terms; ++t) {
+      const uint32_t a_base = sbase + ((t == 2) ? TC_OFF_A1LO : TC_OFF_A1HI);
+      const uint32_t b_base = sbase + ((t == 1) ? TC_OFF_W1LO : TC_OFF_W1HI);
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          umma_ss(tmem, umma_desc(a_base + s * 32), umma_desc(b_base + s * 32), idesc1, acc);
-          acc = 1;
-        }
+      for (int s = 0; s < 4; ++s) {
+        umma_ss(tmem, umma_desc(a_base + s * 32), umma_desc(b_base + s * 32), idesc1, acc);
+        acc = 1;
       }
-      tc_commit(bar1);
     }
+    tc_commit(bar1);
+  };
+  // ---- GEMM2: D2 = H . W2^T  (TS, N=64, K=256 in 16 steps); H hi at column 16s, lo at 16s+8 ----
+  auto issue_g2 = [&]() {
+    tc_fence_after();
+    uint32_t acc = 0;
+    for (int t = 0; t < n_terms; ++t) {
+      const uint32_t b_base = sbase + ((t == 2) ? TC_OFF_W2LO : TC_OFF_W2HI);
+      const uint32_t a_sel = (t == 1) ? 8u : 0u;  // t=1: H_lo . W2_hi
+#pragma unroll
+      for (int s = 0; s < 16; ++s) {
+        const uint32_t b_off = (uint32_t)((s >> 2) * (PF_D * 128) + (s & 3) * 32);
+        umma_ts(tmem + TC_COL_D2, tmem + (uint32_t)(16 * s) + a_sel, umma_desc(b_base + b_off), idesc2, acc);
+        acc = 1;
+      }
+    }
+    tc_commit(bar2);
+  };
+
+  long long tile = blockIdx.x;
+  uint32_t phase = 0;
+  int buf = 0;
+  bool ok = true;
+  if (tile < n_tiles) {
+    prologue(tile, 0);
+    fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    __syncthreads();
+    if (tid == 0) issue_g1();
+  }
+  for (; tile < n_tiles; tile += gridDim.x) {
+    const long long next = tile + gridDim.x;
+    const bool has_next = next < n_tiles;
+    const bool dump_this = (dump != nullptr) && (tile == 0);
     ok = mbar_wait(bar1, phase) && ok;
     tc_fence_after();
-    // ================= epilogue 1: H = gelu(D1 + b1), bf16 hi/lo, in place in TMEM ==========
+    // ============ E1: H = gelu(D1 + b1) as bf16 hi/lo, in place in TMEM ============
     {
-      const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-      const int col0 = (warp >> 2) * 128;
+      const int col0 = cgrp * 64;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
-        const int cc = col0 + c * 32;
-        uint32_t v[32];
-        tmem_ld32(tmem + lane_base + cc, v);
+        const int cc = col0 + c * 16;
+        uint32_t v[16];
+        tmem_ld16(tmem + lane_base + cc, v);
         tc_wait_ld();
-        if (dump != nullptr && blockIdx.x == 0 && tile == blockIdx.x) {
-          const int row = (warp & 3) * 32 + lane;
+        if (dump_this) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) dump[row * 320 + cc + i] = __uint_as_float(v[i]);
+          for (int i = 0; i < 16; ++i) dump[row_t * 320 + cc + i] = __uint_as_float(v[i]);
         }
-        uint32_t hi[16], lo[16];
+        uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float g0 = gelu_erf(__uint_as_float(v[2 * i]) + sb1[cc + 2 * i]);
-          const float g1 = gelu_erf(__uint_as_float(v[2 * i + 1]) + sb1[cc + 2 * i + 1]);
+        for (int i = 0; i < 8; ++i) {
+          const float2 bb = *reinterpret_cast<const float2*>(sb1 + cc + 2 * i);
+          const float g0 = TC_GELU(__uint_as_float(v[2 * i]) + bb.x);
+          const float g1 = TC_GELU(__uint_as_float(v[2 * i + 1]) + bb.y);
           const __nv_bfloat162 hh = __floats2bfloat162_rn(g0, g1);
           const __nv_bfloat162 ll = __floats2bfloat162_rn(g0 - __low2float(hh), g1 - __high2float(hh));
           hi[i] = *reinterpret_cast<const uint32_t*>(&hh);
           lo[i] = *reinterpret_cast<const uint32_t*>(&ll);
         }
-        tmem_st16(tmem + lane_base + cc, hi);
-        tmem_st16(tmem + lane_base + cc + 16, lo);
+        tmem_st8(tmem + lane_base + cc, hi);
+        tmem_st8(tmem + lane_base + cc + 8, lo);
       }
       tc_wait_st();
     }
     tc_fence_before();
     __syncthreads();
-    // ================= GEMM2: D2 = H . W2^T  (TS, N=64, K=256 in 16 steps) ==================
-    if (tid == 0) {
-      tc_fence_after();
-      uint32_t acc = 0;
-      for (int t = 0; t < n_terms; ++t) {
-        const uint32_t b_base = sbase + ((t == 2) ? TC_OFF_W2LO : TC_OFF_W2HI);
-        const uint32_t a_sel = (t == 1) ? 16u : 0u;  // t=1: H_lo . W2_hi
-#pragma unroll
-        for (int s = 0; s < 16; ++s) {
-          const uint32_t a_col = (uint32_t)(32 * (s >> 1) + 8 * (s & 1)) + a_sel;
-          const uint32_t b_off = (uint32_t)((s >> 2) * (PF_D * 128) + (s & 3) * 32);
-          umma_ts(tmem + TC_COL_D2, tmem + a_col, umma_desc(b_base + b_off), idesc2, acc);
-          acc = 1;
-        }
-      }
-      tc_commit(bar2);
-    }
+    if (tid == 0) issue_g2();
+    // ============ P(i+1) while G2(i) runs ============
+    if (has_next) prologue(next, buf ^ 1);
+    fence_proxy_async_smem();
     ok = mbar_wait(bar2, phase) && ok;
     tc_fence_after();
-    phase ^= 1;
-    // ================= epilogue 2: y = x2 + D2 + b2 -> XS ==================================
+    __syncthreads();
+    if (has_next && tid == 0) issue_g1();
+    // ============ E2: y = x2 + D2 + b2 -> XS[buf], while G1(i+1) runs ============
+    float* XS = reinterpret_cast<float*>(sm + TC_OFF_XS + buf * 32768);
     {
-      const int r = (warp & 3) * 32 + lane;
-      const int hf = warp >> 2;
-      uint32_t v[32];
-      tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + TC_COL_D2 + hf * 32, v);
+      uint32_t v[16];
+      tmem_ld16(tmem + lane_base + TC_COL_D2 + cgrp * 16, v);
       tc_wait_ld();
-      if (dump != nullptr && blockIdx.x == 0 && tile == blockIdx.x) {
+      if (dump_this) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) dump[r * 320 + 256 + hf * 32 + i] = __uint_as_float(v[i]);
+        for (int i = 0; i < 16; ++i) dump[row_t * 320 + 256 + cgrp * 16 + i] = __uint_as_float(v[i]);
       }
-      float4* xr = reinterpret_cast<float4*>(XS + r * PF_D);
+      float4* xr = reinterpret_cast<float4*>(XS + row_t * PF_D);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int c = hf * 8 + i;
-        float4 t = xr[xs_chunk(r, c)];
-        t.x += __uint_as_float(v[4 * i + 0]) + sb2[4 * c + 0];
-        t.y += __uint_as_float(v[4 * i + 1]) + sb2[4 * c + 1];
-        t.z += __uint_as_float(v[4 * i + 2]) + sb2[4 * c + 2];
-        t.w += __uint_as_float(v[4 * i + 3]) + sb2[4 * c + 3];
-        xr[xs_chunk(r, c)] = t;
+      for (int i = 0; i < 4; ++i) {
+        const int c = cgrp * 4 + i;
+        const float4 bb = *reinterpret_cast<const float4*>(sb2 + 4 * c);
+        float4 t = xr[xs_chunk(row_t, c)];
+        t.x += __uint_as_float(v[4 * i + 0]) + bb.x;
+        t.y += __uint_as_float(v[4 * i + 1]) + bb.y;
+        t.z += __uint_as_float(v[4 * i + 2]) + bb.z;
+        t.w += __uint_as_float(v[4 * i + 3]) + bb.w;
+        xr[xs_chunk(row_t, c)] = t;
       }
     }
     tc_fence_before();
     __syncthreads();
-    // ================= store: coalesced fp32 rows back to HBM ===============================
-#pragma unroll 1
-    for (int pass = 0; pass < TC_TILE / 32; ++pass) {
-      const int r = pass * 32 + slot;
+    // ============ store: coalesced fp32 rows back to HBM ============
+#pragma unroll
+    for (int pass = 0; pass < TC_TILE / 64; ++pass) {
+      const int r = pass * 64 + slot;
       const long long tok = tile * TC_TILE + r;
       if (tok < n_tok) {
         const float4* xr = reinterpret_cast<const float4*>(XS + r * PF_D);
@@ -409,7 +466,8 @@ k_colapply_ffn_tc(const PfAttnW* __restrict__ Wc, const PfFfnTcW* __restrict__ W
         g[8 + j] = xr[xs_chunk(r, 8 + j)];
       }
     }
-    __syncthreads();
+    phase ^= 1;
+    buf ^= 1;
   }
   if (!ok && err_flag != nullptr) *err_flag = 1;
   // ---- teardown ----
