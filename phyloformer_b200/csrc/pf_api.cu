@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -14,6 +15,7 @@
 #include "pf_common.cuh"
 #include "pf_kernels.cuh"
 #include "pf_ffn_tc.cuh"
+#include "pf_ffn_ws.cuh"
 
 namespace {
 
@@ -52,6 +54,7 @@ struct pf_ctx {
   PfBlockW* blk_dev = nullptr;  // [nb]
   PfFfnTcW* tc_dev = nullptr;   // [nb] bf16 hi/lo smem images for the tcgen05 FFN
   int launches = 0;
+  int ffn_impl = 1;             // 0: pf_ffn_tc.cuh (phased), 1: pf_ffn_ws.cuh (warp-specialised); env PF_FFN_IMPL=tc|ws
   int* err_dev = nullptr;       // set by a kernel whose mbarrier wait timed out
   float* dump_dev = nullptr;    // test hook: raw accumulators of the first FFN tile
   // optional per-kernel timing (pf_profile_*)
@@ -246,7 +249,9 @@ int pf_create(pf_handle* out, const pf_cfg* cfg, const float* const* weights_dev
                                 (int)sizeof(Ffn32Smem)));
   CUDA_TRY(cudaFuncSetAttribute(k_row_attn<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_TRY(cudaFuncSetAttribute(k_row_attn<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  if (const char* e_impl = getenv("PF_FFN_IMPL")) h->ffn_impl = (strcmp(e_impl, "tc") == 0) ? 0 : 1;
   int rc = pf_ffn_tc_init();
+  if (rc == 0) rc = pf_ffn_ws_init();
   if (rc != 0) { cleanup(); return fail(PF_ERR_CUDA, "pf_create: tcgen05 FFN kernel setup failed (%d)", rc); }
   *out = h;
   return PF_OK;
@@ -388,8 +393,12 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
                                                                apply_only ? 1 : 0);
     } else {
       Timed t_(h, PF_KC_FFN, st);
-      const int rc = pf_ffn_tc_launch(&bw->col, h->tc_dev + b, x, colM, L, (int)pl.Pl, n_tok, h->n_sm,
-                                      h->cfg.precision == PF_PREC_BF16 ? 1 : 3, h->err_dev, h->dump_dev, st);
+      const int terms = h->cfg.precision == PF_PREC_BF16 ? 1 : 3;
+      const int rc = h->ffn_impl == 1
+                         ? pf_ffn_ws_launch(&bw->col, h->tc_dev + b, x, colM, L, (int)pl.Pl, B, h->n_sm, terms,
+                                            h->err_dev, h->dump_dev, st)
+                         : pf_ffn_tc_launch(&bw->col, h->tc_dev + b, x, colM, L, (int)pl.Pl, n_tok, h->n_sm, terms,
+                                            h->err_dev, h->dump_dev, st);
       if (rc != 0) return fail(PF_ERR_CUDA, "pf_forward: tcgen05 FFN launch failed (%d)", rc);
     }
     CUDA_TRY(cudaGetLastError());

@@ -1,0 +1,424 @@
+// pf_ffn_ws.cuh -- warp-specialised tcgen05 kernel for column apply + LayerNorm + FFN + residual.
+//
+//   x2 = x1 + M_l qhat + bo ;  x3 = x2 + W2 gelu(W1 LN(x2) + b1) + b2       (model.py:97-104)
+//
+// Same math and the same UMMA operand images as pf_ffn_tc.cuh; what changes is who does what:
+//
+//   warps 0-3   PRODUCER  one thread per token row (row r <-> TMEM lane r).  Loads the row
+//               (16 x LDG.128), applies column attention with the per-site M_l window held in
+//               shared memory, writes x2 + b2 straight into the GEMM2 accumulator in TMEM (the
+//               residual add is then free: GEMM2 accumulates on top of it), LayerNorms, splits
+//               into bf16 hi/lo and stores the GEMM1 A operand (SWIZZLE_128B) in shared memory.
+//   warp  4     MMA       one elected thread issues every tcgen05.mma / tcgen05.commit.
+//   warps 8-15  EPILOGUE  GELU on the GEMM1 accumulator in TMEM, rewritten in place as packed bf16
+//               hi/lo (FFMA2/FMUL2 packed-fp32 math); final rows TMEM -> HBM.
+//
+// A tile is 8 pairs x 16 consecutive sites (128 rows) so that the 16-site window of M_l
+// (16.6 KB) stays resident in shared memory while a CTA walks down the pairs; CTAs own
+// contiguous tile ranges, window-major.  The hidden layer is processed in two 128-unit halves
+// with separate TMEM buffers and barriers, the A operand and the GEMM2 accumulator are double
+// buffered, so the tensor pipe, the producer and the epilogue run concurrently:
+//
+//   TMEM columns   [0,128) D1 half a   [128,256) D1 half b   [256,320) D2 slot 0   [320,384) D2 slot 1
+//   MMA order      G2a(i)  G1a(i+1)  G2b(i)  G1b(i+1)        (in-order issue covers the WAR on D1)
+//   epilogue order E1a(i)  E2(i-1)  E1b(i)
+#pragma once
+#include "pf_ffn_tc.cuh"
+
+#define WS_THREADS 512
+#define WS_G 8    // pairs per tile
+#define WS_S 16   // sites per tile
+#define WS_OFF_A1 131072            // 2 slots x (hi 16 KB + lo 16 KB)
+#define WS_OFF_MWIN 196608          // [16][260] floats
+#define WS_MWIN_BYTES (WS_S * PF_MROW * 4)
+#define WS_OFF_WQ (WS_OFF_MWIN + 16896)   // [64][4] folded column q weights
+#define WS_OFF_BO (WS_OFF_WQ + 1024)      // [64]
+#define WS_OFF_B1 (WS_OFF_BO + 256)       // [256]
+#define WS_OFF_B2 (WS_OFF_B1 + 1024)      // [64]
+#define WS_OFF_QC (WS_OFF_B2 + 256)       // sum_c wq[h][c] (4), bq (4)
+#define WS_OFF_BAR (WS_OFF_QC + 32)       // 12 mbarriers
+#define WS_OFF_TMEM (WS_OFF_BAR + 96)
+#define WS_SMEM_BYTES (WS_OFF_TMEM + 32 + 1024)
+#define WS_COL_D2 256
+
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float a, float b) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void up2(u64 v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// gelu_fast (pf_ffn_tc.cuh) on two values at once with packed fp32 math; returns (g0, g1).
+__device__ __forceinline__ u64 gelu_fast2(float h0, float h1) {
+  const u64 t = pk2(fabsf(h0), fabsf(h1));
+  u64 p = pk2(5.6212996640e-06f, 5.6212996640e-06f);
+  p = fma2(p, t, pk2(5.1055209009e-05f, 5.1055209009e-05f));
+  p = fma2(p, t, pk2(3.9686137011e-05f, 3.9686137011e-05f));
+  p = fma2(p, t, pk2(3.4227392389e-03f, 3.4227392389e-03f));
+  p = fma2(p, t, pk2(2.2076998457e-02f, 2.2076998457e-02f));
+  p = fma2(p, t, pk2(5.2075163037e-02f, 5.2075163037e-02f));
+  p = fma2(p, t, pk2(1.0442737824e+00f, 1.0442737824e+00f));
+  p = mul2(p, p); p = mul2(p, p); p = mul2(p, p); p = mul2(p, p);
+  float p0, p1, r0, r1;
+  up2(p, p0, p1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(p0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(p1));
+  float q0, q1;
+  up2(mul2(pk2(h0, h1), pk2(r0, r1)), q0, q1);
+  return fma2(pk2(fabsf(q0), fabsf(q1)), pk2(-1.f, -1.f), pk2(fmaxf(h0, 0.f), fmaxf(h1, 0.f)));
+}
+
+// bf16 hi/lo split of a packed pair: hi = rn(g), lo = rn(g - hi); both as packed bf16x2 words.
+__device__ __forceinline__ void split2(u64 g, uint32_t& hi, uint32_t& lo) {
+  float g0, g1;
+  up2(g, g0, g1);
+  const __nv_bfloat162 hh = __floats2bfloat162_rn(g0, g1);
+  hi = *reinterpret_cast<const uint32_t*>(&hh);
+  const u64 hf = pk2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u));
+  float l0, l1;
+  up2(fma2(hf, pk2(-1.f, -1.f), g), l0, l1);
+  const __nv_bfloat162 ll = __floats2bfloat162_rn(l0, l1);
+  lo = *reinterpret_cast<const uint32_t*>(&ll);
+}
+
+struct WsTileMap {  // tile index -> rows
+  int L, Pl, nW, nPG;
+  __device__ __forceinline__ void decode(long long t, int& b, int& w, int& pg) const {
+    pg = (int)(t % nPG);
+    const long long bw = t / nPG;
+    w = (int)(bw % nW);
+    b = (int)(bw / nW);
+  }
+};
+
+__global__ void __launch_bounds__(WS_THREADS, 1)
+k_colapply_ffn_ws(const PfAttnW* __restrict__ Wc, const PfFfnTcW* __restrict__ Wt, float* __restrict__ x,
+                  const float* __restrict__ colM, int L, int Pl, int B, int n_terms, int* __restrict__ err_flag,
+                  float* __restrict__ dump) {
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(sm);
+  float* mwin = reinterpret_cast<float*>(sm + WS_OFF_MWIN);
+  float* swq = reinterpret_cast<float*>(sm + WS_OFF_WQ);
+  float* sbo = reinterpret_cast<float*>(sm + WS_OFF_BO);
+  float* sb1 = reinterpret_cast<float*>(sm + WS_OFF_B1);
+  float* sb2 = reinterpret_cast<float*>(sm + WS_OFF_B2);
+  float* sqc = reinterpret_cast<float*>(sm + WS_OFF_QC);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + WS_OFF_TMEM);
+  // barriers: [0,1] a1_full  [2,3] a1_free  [4,5] d2_free  [6,7] g1_done  [8,9] h_full  [10,11] g2_done
+  const uint32_t bars = sbase + WS_OFF_BAR;
+  auto BAR = [&](int i) { return bars + 8u * (uint32_t)i; };
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // ---- one-time setup ----
+  {
+    const int4* src = reinterpret_cast<const int4*>(Wt->w1hi);
+    int4* dst = reinterpret_cast<int4*>(sm);
+    for (int i = tid; i < 131072 / 16; i += WS_THREADS) dst[i] = src[i];
+    if (tid < PF_HID) sb1[tid] = Wt->b1[tid];
+    if (tid < PF_D) {
+      sb2[tid] = Wt->b2[tid];
+      sbo[tid] = Wc->bo[tid];
+#pragma unroll
+      for (int h = 0; h < PF_H; ++h) swq[tid * 4 + h] = Wc->wqk[4 + h][tid];
+    }
+    if (tid < PF_H) {
+      float s = 0.f;
+      for (int c = 0; c < PF_D; ++c) s += Wc->wqk[4 + tid][c];
+      sqc[tid] = s;
+      sqc[4 + tid] = Wc->bqk[4 + tid];
+    }
+  }
+  if (tid == 0) {
+    mbar_init(BAR(0), 128); mbar_init(BAR(1), 128);
+    mbar_init(BAR(2), 1);   mbar_init(BAR(3), 1);
+    mbar_init(BAR(4), 256); mbar_init(BAR(5), 256);
+    mbar_init(BAR(6), 1);   mbar_init(BAR(7), 1);
+    mbar_init(BAR(8), 256); mbar_init(BAR(9), 256);
+    mbar_init(BAR(10), 1);  mbar_init(BAR(11), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + WS_OFF_TMEM), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  WsTileMap tm;
+  tm.L = L; tm.Pl = Pl; tm.nW = (L + WS_S - 1) / WS_S; tm.nPG = (Pl + WS_G - 1) / WS_G;
+  const long long NT = (long long)B * tm.nW * tm.nPG;
+  const long long t_begin = NT * blockIdx.x / gridDim.x;
+  const long long t_end = NT * (blockIdx.x + 1) / gridDim.x;
+  const int n_my = (int)(t_end - t_begin);
+  bool ok = true;
+
+  if (warp < 4) {
+    // =============================== PRODUCER ===============================================
+    const int r = tid;                 // row == TMEM lane
+    const int g = r >> 4, s = r & 15;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    int cur_b = -1, cur_w = -1;
+    for (int it = 0; it < n_my; ++it) {
+      const int a = it & 1;
+      const uint32_t par = (uint32_t)((it >> 1) & 1);
+      int b, w, pg;
+      tm.decode(t_begin + it, b, w, pg);
+      // ---- row load first: the latency overlaps the waits below ----
+      const int pair = pg * WS_G + g, site = w * WS_S + s;
+      const bool valid = (pair < Pl) && (site < L);
+      float xr[PF_D];
+      {
+        const float4* src = reinterpret_cast<const float4*>(x + (((size_t)b * Pl + (valid ? pair : 0)) * L + (valid ? site : 0)) * PF_D);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid) v = src[c];
+          xr[4 * c] = v.x; xr[4 * c + 1] = v.y; xr[4 * c + 2] = v.z; xr[4 * c + 3] = v.w;
+        }
+      }
+      if (b != cur_b || w != cur_w) {  // new site window: reload M_l (producer warps only)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int n_sites = min(WS_S, L - w * WS_S);
+        const float4* src = reinterpret_cast<const float4*>(colM + ((size_t)b * L + (size_t)w * WS_S) * PF_MROW);
+        float4* dst = reinterpret_cast<float4*>(mwin);
+        for (int i = tid; i < n_sites * (PF_MROW / 4); i += 128) dst[i] = src[i];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        cur_b = b; cur_w = w;
+      }
+      const float* mrow = mwin + (valid ? s : 0) * PF_MROW;
+      // ---- column attention: q from LN_col(x1); the centred row is consumed on the fly ----
+      float mean, rstd;
+      float qh[PF_H];
+      {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < PF_D; c += 4) { s0 += xr[c]; s1 += xr[c + 1]; s2 += xr[c + 2]; s3 += xr[c + 3]; }
+        mean = ((s0 + s1) + (s2 + s3)) * (1.0f / PF_D);
+        float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < PF_D; c += 4) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float d = xr[c + k] - mean;
+            const float4 wv = *reinterpret_cast<const float4*>(swq + 4 * (c + k));
+            d0 = fmaf(wv.x, d, d0); d1 = fmaf(wv.y, d, d1); d2 = fmaf(wv.z, d, d2); d3 = fmaf(wv.w, d, d3);
+            if (k == 0) q0 = fmaf(d, d, q0); else if (k == 1) q1 = fmaf(d, d, q1);
+            else if (k == 2) q2 = fmaf(d, d, q2); else q3 = fmaf(d, d, q3);
+          }
+        }
+        rstd = 1.0f / sqrtf(fmaf((q0 + q1) + (q2 + q3), 1.0f / PF_D, 1e-5f));
+        const float4 qi = *reinterpret_cast<const float4*>(mrow + 256);
+        qh[0] = phi_elu1(fmaf(rstd, d0, sqc[4])) * qi.x;
+        qh[1] = phi_elu1(fmaf(rstd, d1, sqc[5])) * qi.y;
+        qh[2] = phi_elu1(fmaf(rstd, d2, sqc[6])) * qi.z;
+        qh[3] = phi_elu1(fmaf(rstd, d3, sqc[7])) * qi.w;
+      }
+#pragma unroll
+      for (int c = 0; c < PF_D; ++c) {
+        const float4 m = *reinterpret_cast<const float4*>(mrow + 4 * c);
+        float acc = sbo[c];
+        acc = fmaf(m.x, qh[0], acc); acc = fmaf(m.y, qh[1], acc); acc = fmaf(m.z, qh[2], acc); acc = fmaf(m.w, qh[3], acc);
+        xr[c] += acc;   // x2
+      }
+      // ---- wait for the slot, then seed the GEMM2 accumulator with x2 + b2 ----
+      ok = mbar_wait(BAR(2 + a), par ^ 1) && ok;   // A1[a] free (G1 of tile it-2 done)
+      ok = mbar_wait(BAR(4 + a), par ^ 1) && ok;   // D2[a] free (E2 of tile it-2 done)
+      tc_fence_after();
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        uint32_t v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(xr[16 * c4 + i] + sb2[16 * c4 + i]);
+        tmem_st16(tmem + lane_base + WS_COL_D2 + 64 * a + 16 * c4, v);
+      }
+      // ---- LN_ffn (affine folded into W1/b1), bf16 hi/lo split -> A1[a] ----
+      {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < PF_D; c += 4) { s0 += xr[c]; s1 += xr[c + 1]; s2 += xr[c + 2]; s3 += xr[c + 3]; }
+        mean = ((s0 + s1) + (s2 + s3)) * (1.0f / PF_D);
+        float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < PF_D; c += 4) {
+          const float d0 = xr[c] - mean, d1 = xr[c + 1] - mean, d2 = xr[c + 2] - mean, d3 = xr[c + 3] - mean;
+          q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+        }
+        rstd = 1.0f / sqrtf(fmaf((q0 + q1) + (q2 + q3), 1.0f / PF_D, 1e-5f));
+      }
+      {
+        unsigned char* a1hi = sm + WS_OFF_A1 + a * 32768;
+        unsigned char* a1lo = a1hi + 16384;
+        const uint32_t rowoff = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+        const u64 nm = pk2(-mean, -mean), rs = pk2(rstd, rstd);
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {  // 16-byte chunk = 8 channels
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const u64 nv = mul2(add2(pk2(xr[8 * ch + 2 * i], xr[8 * ch + 2 * i + 1]), nm), rs);
+            split2(nv, hi[i], lo[i]);
+          }
+          const uint32_t off = rowoff + (uint32_t)(((ch ^ r) & 7) << 4);
+          *reinterpret_cast<uint4*>(a1hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(a1lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+      tc_wait_st();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(BAR(0 + a));
+    }
+  } else if (warp == 4) {
+    // =============================== MMA ISSUER =============================================
+    if (lane == 0 && n_my > 0) {
+      const uint32_t idesc1 = umma_idesc(128, 128), idesc2 = umma_idesc(128, 64);
+      auto issue_g1 = [&](int a, int half) {  // D1[half] = A1[a] . W1[half*128 .. +128)^T
+        const uint32_t a_hi = sbase + WS_OFF_A1 + a * 32768, a_lo = a_hi + 16384;
+        uint32_t acc = 0;
+        for (int t = 0; t < n_terms; ++t) {
+          const uint32_t a_base = (t == 2) ? a_lo : a_hi;
+          const uint32_t b_base = sbase + ((t == 1) ? TC_OFF_W1LO : TC_OFF_W1HI) + half * 16384;
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            umma_ss(tmem + 128 * half, umma_desc(a_base + s * 32), umma_desc(b_base + s * 32), idesc1, acc);
+            acc = 1;
+          }
+        }
+      };
+      auto issue_g2 = [&](int a, int half) {  // D2[a] += H[half] . W2[:, half*128 .. +128)^T
+        for (int t = 0; t < n_terms; ++t) {
+          const uint32_t b_base = sbase + ((t == 2) ? TC_OFF_W2LO : TC_OFF_W2HI);
+          const uint32_t a_sel = (t == 1) ? 8u : 0u;
+#pragma unroll
+          for (int s8 = 0; s8 < 8; ++s8) {
+            const int s = half * 8 + s8;
+            const uint32_t b_off = (uint32_t)((s >> 2) * (PF_D * 128) + (s & 3) * 32);
+            umma_ts(tmem + WS_COL_D2 + 64 * a, tmem + (uint32_t)(16 * s) + a_sel, umma_desc(b_base + b_off), idesc2, 1u);
+          }
+        }
+      };
+      ok = mbar_wait(BAR(0), 0) && ok;  // A1[0] + D2[0] seeded
+      tc_fence_after();
+      issue_g1(0, 0); tc_commit(BAR(6));
+      issue_g1(0, 1); tc_commit(BAR(7)); tc_commit(BAR(2));
+      for (int it = 0; it < n_my; ++it) {
+        const int a = it & 1, an = a ^ 1;
+        const uint32_t ph = (uint32_t)(it & 1);
+        const bool has_next = it + 1 < n_my;
+        ok = mbar_wait(BAR(8), ph) && ok;   // H half a ready
+        tc_fence_after();
+        issue_g2(a, 0);
+        if (has_next) {
+          ok = mbar_wait(BAR(0 + an), (uint32_t)(((it + 1) >> 1) & 1)) && ok;
+          tc_fence_after();
+          issue_g1(an, 0); tc_commit(BAR(6));
+        }
+        ok = mbar_wait(BAR(9), ph) && ok;   // H half b ready
+        tc_fence_after();
+        issue_g2(a, 1); tc_commit(BAR(10 + a));
+        if (has_next) {
+          issue_g1(an, 1); tc_commit(BAR(7)); tc_commit(BAR(2 + an));
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // =============================== EPILOGUE ===============================================
+    const int q = warp & 3, chf = (warp - 8) >> 2;   // TMEM lane quadrant, column half
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int r = q * 32 + lane, g = r >> 4, s = r & 15;
+    auto e1 = [&](int half, bool dump_this) {  // D1[half] cols [64 chf, +64) -> gelu -> bf16 hi/lo in place
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int cc = half * 128 + chf * 64 + c * 16;   // TMEM column == hidden unit
+        uint32_t v[16];
+        tmem_ld16(tmem + lane_base + cc, v);
+        tc_wait_ld();
+        if (dump_this) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) dump[r * 320 + cc + i] = __uint_as_float(v[i]);
+        }
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 bb = *reinterpret_cast<const float2*>(sb1 + cc + 2 * i);
+          split2(gelu_fast2(__uint_as_float(v[2 * i]) + bb.x, __uint_as_float(v[2 * i + 1]) + bb.y), hi[i], lo[i]);
+        }
+        tmem_st8(tmem + lane_base + cc, hi);
+        tmem_st8(tmem + lane_base + cc + 8, lo);
+      }
+      tc_wait_st();
+      tc_fence_before();
+    };
+    auto e2 = [&](int it) {  // D2[it&1] cols [32 chf, +32) -> HBM
+      const int a = it & 1;
+      ok = mbar_wait(BAR(10 + a), (uint32_t)((it >> 1) & 1)) && ok;
+      tc_fence_after();
+      int b, w, pg;
+      tm.decode(t_begin + it, b, w, pg);
+      const int pair = pg * WS_G + g, site = w * WS_S + s;
+      const bool valid = (pair < Pl) && (site < L);
+      float4* dst = reinterpret_cast<float4*>(x + (((size_t)b * Pl + (valid ? pair : 0)) * L + (valid ? site : 0)) * PF_D) + 8 * chf;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[16];
+        tmem_ld16(tmem + lane_base + WS_COL_D2 + 64 * a + 32 * chf + 16 * c, v);
+        tc_wait_ld();
+        if (dump != nullptr && blockIdx.x == 0 && it == 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) dump[r * 320 + 256 + 32 * chf + 16 * c + i] = __uint_as_float(v[i]);
+        }
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            dst[4 * c + i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                         __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(BAR(4 + a));
+    };
+    for (int it = 0; it < n_my; ++it) {
+      const uint32_t ph = (uint32_t)(it & 1);
+      const bool dump_this = (dump != nullptr) && blockIdx.x == 0 && it == 0;
+      ok = mbar_wait(BAR(6), ph) && ok;
+      tc_fence_after();
+      e1(0, dump_this);
+      mbar_arrive(BAR(8));
+      if (it > 0) e2(it - 1);
+      ok = mbar_wait(BAR(7), ph) && ok;
+      tc_fence_after();
+      e1(1, dump_this);
+      mbar_arrive(BAR(9));
+    }
+    if (n_my > 0) e2(n_my - 1);
+  }
+  if (!ok && err_flag != nullptr) *err_flag = 2;
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+inline int pf_ffn_ws_init() {
+  return (int)cudaFuncSetAttribute(k_colapply_ffn_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
+}
+
+inline int pf_ffn_ws_launch(const PfAttnW* Wc, const PfFfnTcW* Wt, float* x, const float* colM, int L, int Pl, int B,
+                            int n_sm, int n_terms, int* err_flag, float* dump, cudaStream_t st) {
+  const long long nt = (long long)B * ((L + WS_S - 1) / WS_S) * ((Pl + WS_G - 1) / WS_G);
+  const int grid = (int)(nt < n_sm ? nt : n_sm);
+  k_colapply_ffn_ws<<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(Wc, Wt, x, colM, L, Pl, B, n_terms, err_flag, dump);
+  return (int)cudaGetLastError();
+}
