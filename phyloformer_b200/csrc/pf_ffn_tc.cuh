@@ -226,7 +226,8 @@ k_colapply_ffn_tc(const PfAttnW* __restrict__ Wc, const PfFfnTcW* __restrict__ W
                   const float* __restrict__ colM, int L, int Pl, long long n_tok, int n_terms,
                   int* __restrict__ err_flag, float* __restrict__ dump) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
-  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  // keep the pointer derived from the __shared__ array so that accesses compile to LDS/STS
+  unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(sm);
   float* sb1 = reinterpret_cast<float*>(sm + TC_OFF_B1);
   float* sb2 = reinterpret_cast<float*>(sm + TC_OFF_B2);

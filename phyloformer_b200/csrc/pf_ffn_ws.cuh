@@ -100,7 +100,8 @@ k_colapply_ffn_ws(const PfAttnW* __restrict__ Wc, const PfFfnTcW* __restrict__ W
                   const float* __restrict__ colM, int L, int Pl, int B, int n_terms, int* __restrict__ err_flag,
                   float* __restrict__ dump) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
-  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  // keep the pointer derived from the __shared__ array so that accesses compile to LDS/STS
+  unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(sm);
   float* mwin = reinterpret_cast<float*>(sm + WS_OFF_MWIN);
   float* swq = reinterpret_cast<float*>(sm + WS_OFF_WQ);
@@ -337,22 +338,30 @@ k_colapply_ffn_ws(const PfAttnW* __restrict__ Wc, const PfFfnTcW* __restrict__ W
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int r = q * 32 + lane, g = r >> 4, s = r & 15;
     auto e1 = [&](int half, bool dump_this) {  // D1[half] cols [64 chf, +64) -> gelu -> bf16 hi/lo in place
-#pragma unroll 1
+      const int c0 = half * 128 + chf * 64;              // TMEM column == hidden unit
+      uint32_t v[2][16];
+      tmem_ld16(tmem + lane_base + c0, v[0]);
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const int cc = half * 128 + chf * 64 + c * 16;   // TMEM column == hidden unit
-        uint32_t v[16];
-        tmem_ld16(tmem + lane_base + cc, v);
+        const int cc = c0 + c * 16;
+        float bias[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 bb = *reinterpret_cast<const float4*>(sb1 + cc + 4 * i);
+          bias[4 * i] = bb.x; bias[4 * i + 1] = bb.y; bias[4 * i + 2] = bb.z; bias[4 * i + 3] = bb.w;
+        }
         tc_wait_ld();
+        if (c < 3) tmem_ld16(tmem + lane_base + cc + 16, v[(c + 1) & 1]);   // prefetch the next 16 columns
+        const uint32_t(&vc)[16] = v[c & 1];
         if (dump_this) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) dump[r * 320 + cc + i] = __uint_as_float(v[i]);
+          for (int i = 0; i < 16; ++i) dump[r * 320 + cc + i] = __uint_as_float(vc[i]);
         }
         uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float2 bb = *reinterpret_cast<const float2*>(sb1 + cc + 2 * i);
-          split2(gelu_fast2(__uint_as_float(v[2 * i]) + bb.x, __uint_as_float(v[2 * i + 1]) + bb.y), hi[i], lo[i]);
-        }
+        for (int i = 0; i < 8; ++i)
+          split2(gelu_fast2(__uint_as_float(vc[2 * i]) + bias[2 * i], __uint_as_float(vc[2 * i + 1]) + bias[2 * i + 1]),
+                 hi[i], lo[i]);
         tmem_st8(tmem + lane_base + cc, hi);
         tmem_st8(tmem + lane_base + cc + 8, lo);
       }
