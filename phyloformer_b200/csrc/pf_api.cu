@@ -53,8 +53,10 @@ struct pf_ctx {
   PfHeadW* head_dev = nullptr;
   PfBlockW* blk_dev = nullptr;  // [nb]
   PfFfnTcW* tc_dev = nullptr;   // [nb] bf16 hi/lo smem images for the tcgen05 FFN
+  std::vector<PfFfnConst> ffn_const;  // [nb] host copies passed as __grid_constant__ kernel parameters
   int launches = 0;
   int ffn_impl = 1;             // 0: pf_ffn_tc.cuh (phased), 1: pf_ffn_ws.cuh (warp-specialised); env PF_FFN_IMPL=tc|ws
+  int ws_prof = 0;              // env PF_WS_PROF=1: role timing into the dump buffer (test hook)
   int* err_dev = nullptr;       // set by a kernel whose mbarrier wait timed out
   float* dump_dev = nullptr;    // test hook: raw accumulators of the first FFN tile
   // optional per-kernel timing (pf_profile_*)
@@ -230,6 +232,14 @@ int pf_create(pf_handle* out, const pf_cfg* cfg, const float* const* weights_dev
     pack_attn(hw, base + 8, base + 18, &blk[b].col);
     pack_ffn(hw, base + 22, base + 20, &blk[b].ffn);
     pf_pack_ffn_tc(blk[b].ffn, &tc[b]);
+    PfFfnConst kc;
+    for (int c = 0; c < PF_D; ++c) {
+      for (int hh = 0; hh < PF_H; ++hh) kc.wq[c][hh] = blk[b].col.wqk[4 + hh][c];
+      kc.bo[c] = blk[b].col.bo[c];
+      kc.b2[c] = blk[b].ffn.b2[c];
+    }
+    for (int hh = 0; hh < PF_H; ++hh) kc.bq[hh] = blk[b].col.bqk[4 + hh];
+    h->ffn_const.push_back(kc);
   }
   auto cleanup = [&]() { pf_destroy(h); };
   cudaError_t e;
@@ -250,6 +260,7 @@ int pf_create(pf_handle* out, const pf_cfg* cfg, const float* const* weights_dev
   CUDA_TRY(cudaFuncSetAttribute(k_row_attn<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_TRY(cudaFuncSetAttribute(k_row_attn<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   if (const char* e_impl = getenv("PF_FFN_IMPL")) h->ffn_impl = (strcmp(e_impl, "tc") == 0) ? 0 : 1;
+  if (const char* e_prof = getenv("PF_WS_PROF")) h->ws_prof = atoi(e_prof);
   int rc = pf_ffn_tc_init();
   if (rc == 0) rc = pf_ffn_ws_init();
   if (rc != 0) { cleanup(); return fail(PF_ERR_CUDA, "pf_create: tcgen05 FFN kernel setup failed (%d)", rc); }
@@ -395,8 +406,8 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
       Timed t_(h, PF_KC_FFN, st);
       const int terms = h->cfg.precision == PF_PREC_BF16 ? 1 : 3;
       const int rc = h->ffn_impl == 1
-                         ? pf_ffn_ws_launch(&bw->col, h->tc_dev + b, x, colM, L, (int)pl.Pl, B, h->n_sm, terms,
-                                            h->err_dev, h->dump_dev, st)
+                         ? pf_ffn_ws_launch(h->ffn_const[b], h->tc_dev + b, x, colM, L, (int)pl.Pl, B, h->n_sm, terms,
+                                            h->err_dev, h->dump_dev, h->ws_prof, st)
                          : pf_ffn_tc_launch(&bw->col, h->tc_dev + b, x, colM, L, (int)pl.Pl, n_tok, h->n_sm, terms,
                                             h->err_dev, h->dump_dev, st);
       if (rc != 0) return fail(PF_ERR_CUDA, "pf_forward: tcgen05 FFN launch failed (%d)", rc);

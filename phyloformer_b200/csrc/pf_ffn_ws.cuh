@@ -4,13 +4,13 @@
 //
 // Same math and the same UMMA operand images as pf_ffn_tc.cuh; what changes is who does what:
 //
-//   warps 0-3   PRODUCER  one thread per token row (row r <-> TMEM lane r).  Loads the row
+//   warps 8-11  PRODUCER  one thread per token row (row r <-> TMEM lane r).  Loads the row
 //               (16 x LDG.128), applies column attention with the per-site M_l window held in
 //               shared memory, writes x2 + b2 straight into the GEMM2 accumulator in TMEM (the
 //               residual add is then free: GEMM2 accumulates on top of it), LayerNorms, splits
 //               into bf16 hi/lo and stores the GEMM1 A operand (SWIZZLE_128B) in shared memory.
-//   warp  4     MMA       one elected thread issues every tcgen05.mma / tcgen05.commit.
-//   warps 8-15  EPILOGUE  GELU on the GEMM1 accumulator in TMEM, rewritten in place as packed bf16
+//   warp  12    MMA       one elected thread issues every tcgen05.mma / tcgen05.commit.
+//   warps 0-7   EPILOGUE  GELU on the GEMM1 accumulator in TMEM, rewritten in place as packed bf16
 //               hi/lo (FFMA2/FMUL2 packed-fp32 math); final rows TMEM -> HBM.
 //
 // A tile is 8 pairs x 16 consecutive sites (128 rows) so that the 16-site window of M_l
@@ -19,7 +19,7 @@
 // with separate TMEM buffers and barriers, the A operand and the GEMM2 accumulator are double
 // buffered, so the tensor pipe, the producer and the epilogue run concurrently:
 //
-//   TMEM columns   [0,128) D1 half a   [128,256) D1 half b   [256,320) D2 slot 0   [320,384) D2 slot 1
+//   TMEM columns   [0,128) D1 half a   [128,256) D1 half b   [256,448) D2, 3 slots of 64 columns
 //   MMA order      G2a(i)  G1a(i+1)  G2b(i)  G1b(i+1)        (in-order issue covers the WAR on D1)
 //   epilogue order E1a(i)  E2(i-1)  E1b(i)
 #pragma once
@@ -36,10 +36,20 @@
 #define WS_OFF_B1 (WS_OFF_BO + 256)       // [256]
 #define WS_OFF_B2 (WS_OFF_B1 + 1024)      // [64]
 #define WS_OFF_QC (WS_OFF_B2 + 256)       // sum_c wq[h][c] (4), bq (4)
-#define WS_OFF_BAR (WS_OFF_QC + 32)       // 12 mbarriers
-#define WS_OFF_TMEM (WS_OFF_BAR + 96)
+#define WS_OFF_BAR (WS_OFF_QC + 32)       // 14 mbarriers
+#define WS_OFF_TMEM (WS_OFF_BAR + 112)
 #define WS_SMEM_BYTES (WS_OFF_TMEM + 32 + 1024)
 #define WS_COL_D2 256
+
+// Small per-block parameters the producer reads with compile-time indices: passed by value as a
+// __grid_constant__ kernel parameter so that they sit in the constant bank and feed FFMA
+// operands directly (no shared-memory loads, no registers).
+struct PfFfnConst {
+  float wq[PF_D][PF_H];  // folded column-attention q weights [channel][head]
+  float bo[PF_D];        // column out_proj bias
+  float b2[PF_D];        // ffn.3 bias
+  float bq[PF_H];        // folded q bias
+};
 
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pk2(float a, float b) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
@@ -48,6 +58,21 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f3
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void ldg256(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -95,8 +120,9 @@ struct WsTileMap {  // tile index -> rows
   }
 };
 
+template <bool PROF>
 __global__ void __launch_bounds__(WS_THREADS, 1)
-k_colapply_ffn_ws(const PfAttnW* __restrict__ Wc, const PfFfnTcW* __restrict__ Wt, float* __restrict__ x,
+k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restrict__ Wt, float* __restrict__ x,
                   const float* __restrict__ colM, int L, int Pl, int B, int n_terms, int* __restrict__ err_flag,
                   float* __restrict__ dump) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
@@ -104,13 +130,9 @@ k_colapply_ffn_ws(const PfAttnW* __restrict__ Wc, const PfFfnTcW* __restrict__ W
   unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(sm);
   float* mwin = reinterpret_cast<float*>(sm + WS_OFF_MWIN);
-  float* swq = reinterpret_cast<float*>(sm + WS_OFF_WQ);
-  float* sbo = reinterpret_cast<float*>(sm + WS_OFF_BO);
   float* sb1 = reinterpret_cast<float*>(sm + WS_OFF_B1);
-  float* sb2 = reinterpret_cast<float*>(sm + WS_OFF_B2);
-  float* sqc = reinterpret_cast<float*>(sm + WS_OFF_QC);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + WS_OFF_TMEM);
-  // barriers: [0,1] a1_full  [2,3] a1_free  [4,5] d2_free  [6,7] g1_done  [8,9] h_full  [10,11] g2_done
+  // barriers: [0,1] a1_full  [2,3] a1_free  [4..6] d2_free  [7,8] g1_done  [9,10] h_full  [11..13] g2_done
   const uint32_t bars = sbase + WS_OFF_BAR;
   auto BAR = [&](int i) { return bars + 8u * (uint32_t)i; };
 
@@ -122,29 +144,17 @@ k_colapply_ffn_ws(const PfAttnW* __restrict__ Wc, const PfFfnTcW* __restrict__ W
     int4* dst = reinterpret_cast<int4*>(sm);
     for (int i = tid; i < 131072 / 16; i += WS_THREADS) dst[i] = src[i];
     if (tid < PF_HID) sb1[tid] = Wt->b1[tid];
-    if (tid < PF_D) {
-      sb2[tid] = Wt->b2[tid];
-      sbo[tid] = Wc->bo[tid];
-#pragma unroll
-      for (int h = 0; h < PF_H; ++h) swq[tid * 4 + h] = Wc->wqk[4 + h][tid];
-    }
-    if (tid < PF_H) {
-      float s = 0.f;
-      for (int c = 0; c < PF_D; ++c) s += Wc->wqk[4 + tid][c];
-      sqc[tid] = s;
-      sqc[4 + tid] = Wc->bqk[4 + tid];
-    }
   }
   if (tid == 0) {
     mbar_init(BAR(0), 128); mbar_init(BAR(1), 128);
     mbar_init(BAR(2), 1);   mbar_init(BAR(3), 1);
-    mbar_init(BAR(4), 256); mbar_init(BAR(5), 256);
-    mbar_init(BAR(6), 1);   mbar_init(BAR(7), 1);
-    mbar_init(BAR(8), 256); mbar_init(BAR(9), 256);
-    mbar_init(BAR(10), 1);  mbar_init(BAR(11), 1);
+    mbar_init(BAR(4), 256); mbar_init(BAR(5), 256); mbar_init(BAR(6), 256);
+    mbar_init(BAR(7), 1);   mbar_init(BAR(8), 1);
+    mbar_init(BAR(9), 256); mbar_init(BAR(10), 256);
+    mbar_init(BAR(11), 1);  mbar_init(BAR(12), 1);  mbar_init(BAR(13), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == 12) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + WS_OFF_TMEM), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -161,12 +171,27 @@ k_colapply_ffn_ws(const PfAttnW* __restrict__ Wc, const PfFfnTcW* __restrict__ W
   const long long t_end = NT * (blockIdx.x + 1) / gridDim.x;
   const int n_my = (int)(t_end - t_begin);
   bool ok = true;
+  // optional role timing (test hook PF_WS_PROF=1): cycles spent in each wait, per role leader
+  long long tw[7] = {0, 0, 0, 0, 0, 0, 0};
+  const long long t_start = PROF ? clock64() : 0;
+  auto TIC = [&]() -> long long { return PROF ? clock64() : 0; };
+  auto TOC = [&](int slot, long long t0) { if (PROF) tw[slot] += clock64() - t0; };
+  auto WAIT = [&](int slot, uint32_t bar, uint32_t parity) {
+    if (PROF) {
+      const long long t0 = clock64();
+      ok = mbar_wait(bar, parity) && ok;
+      tw[slot] += clock64() - t0;
+    } else {
+      ok = mbar_wait(bar, parity) && ok;
+    }
+  };
 
-  if (warp < 4) {
+  if (warp >= 8 && warp < 12) {
     // =============================== PRODUCER ===============================================
-    const int r = tid;                 // row == TMEM lane
+    const int ptid = tid - 256;        // 0..127
+    const int r = ptid;                // row == TMEM lane
     const int g = r >> 4, s = r & 15;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     int cur_b = -1, cur_w = -1;
     for (int it = 0; it < n_my; ++it) {
       const int a = it & 1;
@@ -178,12 +203,13 @@ k_colapply_ffn_ws(const PfAttnW* __restrict__ Wc, const PfFfnTcW* __restrict__ W
       const bool valid = (pair < Pl) && (site < L);
       float xr[PF_D];
       {
-        const float4* src = reinterpret_cast<const float4*>(x + (((size_t)b * Pl + (valid ? pair : 0)) * L + (valid ? site : 0)) * PF_D);
+        const float* src = x + (((size_t)b * Pl + (valid ? pair : 0)) * L + (valid ? site : 0)) * PF_D;
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (valid) v = src[c];
-          xr[4 * c] = v.x; xr[4 * c + 1] = v.y; xr[4 * c + 2] = v.z; xr[4 * c + 3] = v.w;
+        for (int c = 0; c < 8; ++c) {
+          float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (valid) ldg256(src + 8 * c, v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) xr[8 * c + i] = v[i];
         }
       }
       if (b != cur_b || w != cur_w) {  // new site window: reload M_l (producer warps only)
@@ -191,11 +217,12 @@ k_colapply_ffn_ws(const PfAttnW* __restrict__ Wc, const PfFfnTcW* __restrict__ W
         const int n_sites = min(WS_S, L - w * WS_S);
         const float4* src = reinterpret_cast<const float4*>(colM + ((size_t)b * L + (size_t)w * WS_S) * PF_MROW);
         float4* dst = reinterpret_cast<float4*>(mwin);
-        for (int i = tid; i < n_sites * (PF_MROW / 4); i += 128) dst[i] = src[i];
+        for (int i = ptid; i < n_sites * (PF_MROW / 4); i += 128) dst[i] = src[i];
         asm volatile("bar.sync 1, 128;" ::: "memory");
         cur_b = b; cur_w = w;
       }
       const float* mrow = mwin + (valid ? s : 0) * PF_MROW;
+      const long long tp0 = TIC();
       // ---- column attention: q from LN_col(x1); the centred row is consumed on the fly ----
       float mean, rstd;
       float qh[PF_H];
@@ -211,36 +238,38 @@ k_colapply_ffn_ws(const PfAttnW* __restrict__ Wc, const PfFfnTcW* __restrict__ W
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const float d = xr[c + k] - mean;
-            const float4 wv = *reinterpret_cast<const float4*>(swq + 4 * (c + k));
-            d0 = fmaf(wv.x, d, d0); d1 = fmaf(wv.y, d, d1); d2 = fmaf(wv.z, d, d2); d3 = fmaf(wv.w, d, d3);
+            d0 = fmaf(kc.wq[c + k][0], d, d0); d1 = fmaf(kc.wq[c + k][1], d, d1);
+            d2 = fmaf(kc.wq[c + k][2], d, d2); d3 = fmaf(kc.wq[c + k][3], d, d3);
             if (k == 0) q0 = fmaf(d, d, q0); else if (k == 1) q1 = fmaf(d, d, q1);
             else if (k == 2) q2 = fmaf(d, d, q2); else q3 = fmaf(d, d, q3);
           }
         }
         rstd = 1.0f / sqrtf(fmaf((q0 + q1) + (q2 + q3), 1.0f / PF_D, 1e-5f));
+        if (PROF) { if (rstd > -1.f) TOC(2, tp0); }
         const float4 qi = *reinterpret_cast<const float4*>(mrow + 256);
-        qh[0] = phi_elu1(fmaf(rstd, d0, sqc[4])) * qi.x;
-        qh[1] = phi_elu1(fmaf(rstd, d1, sqc[5])) * qi.y;
-        qh[2] = phi_elu1(fmaf(rstd, d2, sqc[6])) * qi.z;
-        qh[3] = phi_elu1(fmaf(rstd, d3, sqc[7])) * qi.w;
+        qh[0] = phi_elu1(fmaf(rstd, d0, kc.bq[0])) * qi.x;
+        qh[1] = phi_elu1(fmaf(rstd, d1, kc.bq[1])) * qi.y;
+        qh[2] = phi_elu1(fmaf(rstd, d2, kc.bq[2])) * qi.z;
+        qh[3] = phi_elu1(fmaf(rstd, d3, kc.bq[3])) * qi.w;
       }
 #pragma unroll
       for (int c = 0; c < PF_D; ++c) {
         const float4 m = *reinterpret_cast<const float4*>(mrow + 4 * c);
-        float acc = sbo[c];
+        float acc = kc.bo[c];
         acc = fmaf(m.x, qh[0], acc); acc = fmaf(m.y, qh[1], acc); acc = fmaf(m.z, qh[2], acc); acc = fmaf(m.w, qh[3], acc);
         xr[c] += acc;   // x2
       }
       // ---- wait for the slot, then seed the GEMM2 accumulator with x2 + b2 ----
-      ok = mbar_wait(BAR(2 + a), par ^ 1) && ok;   // A1[a] free (G1 of tile it-2 done)
-      ok = mbar_wait(BAR(4 + a), par ^ 1) && ok;   // D2[a] free (E2 of tile it-2 done)
+      const int d = it % 3;                        // GEMM2 accumulator slot (3-deep ring)
+      WAIT(0, BAR(2 + a), par ^ 1);   // A1[a] free (G1 of tile it-2 done)
+      WAIT(1, BAR(4 + d), (uint32_t)(((it / 3) & 1) ^ 1));   // D2[d] free (E2 of tile it-3 done)
       tc_fence_after();
 #pragma unroll
       for (int c4 = 0; c4 < 4; ++c4) {
         uint32_t v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(xr[16 * c4 + i] + sb2[16 * c4 + i]);
-        tmem_st16(tmem + lane_base + WS_COL_D2 + 64 * a + 16 * c4, v);
+        for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(xr[16 * c4 + i] + kc.b2[16 * c4 + i]);
+        tmem_st16(tmem + lane_base + WS_COL_D2 + 64 * d + 16 * c4, v);
       }
       // ---- LN_ffn (affine folded into W1/b1), bf16 hi/lo split -> A1[a] ----
       {
@@ -274,85 +303,109 @@ k_colapply_ffn_ws(const PfAttnW* __restrict__ Wc, const PfFfnTcW* __restrict__ W
           *reinterpret_cast<uint4*>(a1lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
       }
-      tc_wait_st();
+      { const long long t0 = TIC(); tc_wait_st(); TOC(3, t0); }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(BAR(0 + a));
     }
-  } else if (warp == 4) {
+  } else if (warp == 12) {
     // =============================== MMA ISSUER =============================================
-    if (lane == 0 && n_my > 0) {
+    // The whole warp walks the loop (so descriptors live in uniform registers); one elected lane
+    // issues.  Descriptors are built once: per k-step only the 16-byte-unit address field moves.
+    if (n_my > 0) {
       const uint32_t idesc1 = umma_idesc(128, 128), idesc2 = umma_idesc(128, 64);
+      const u64 dA00 = umma_desc(sbase + WS_OFF_A1), dA01 = umma_desc(sbase + WS_OFF_A1 + 16384);
+      const u64 dA10 = umma_desc(sbase + WS_OFF_A1 + 32768), dA11 = umma_desc(sbase + WS_OFF_A1 + 49152);
+      const u64 dW1h = umma_desc(sbase + TC_OFF_W1HI), dW1l = umma_desc(sbase + TC_OFF_W1LO);
+      const u64 dW2h = umma_desc(sbase + TC_OFF_W2HI), dW2l = umma_desc(sbase + TC_OFF_W2LO);
       auto issue_g1 = [&](int a, int half) {  // D1[half] = A1[a] . W1[half*128 .. +128)^T
-        const uint32_t a_hi = sbase + WS_OFF_A1 + a * 32768, a_lo = a_hi + 16384;
-        uint32_t acc = 0;
-        for (int t = 0; t < n_terms; ++t) {
-          const uint32_t a_base = (t == 2) ? a_lo : a_hi;
-          const uint32_t b_base = sbase + ((t == 1) ? TC_OFF_W1LO : TC_OFF_W1HI) + half * 16384;
+        const u64 ah = a ? dA10 : dA00, al = a ? dA11 : dA01;
+        const u64 hoff = (u64)(half * (16384 >> 4));
+        const uint32_t dcol = tmem + 128 * half;
 #pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            umma_ss(tmem + 128 * half, umma_desc(a_base + s * 32), umma_desc(b_base + s * 32), idesc1, acc);
-            acc = 1;
+        for (int t = 0; t < 3; ++t) {
+          if (t < n_terms) {
+            const u64 da = (t == 2) ? al : ah;
+            const u64 db = ((t == 1) ? dW1l : dW1h) + hoff;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) umma_ss(dcol, da + 2 * s, db + 2 * s, idesc1, (t | s) ? 1u : 0u);
           }
         }
       };
-      auto issue_g2 = [&](int a, int half) {  // D2[a] += H[half] . W2[:, half*128 .. +128)^T
-        for (int t = 0; t < n_terms; ++t) {
-          const uint32_t b_base = sbase + ((t == 2) ? TC_OFF_W2LO : TC_OFF_W2HI);
-          const uint32_t a_sel = (t == 1) ? 8u : 0u;
+      auto issue_g2 = [&](int d, int half) {  // D2[slot d] += H[half] . W2[:, half*128 .. +128)^T
+        const uint32_t dcol = tmem + WS_COL_D2 + 64 * d;
 #pragma unroll
-          for (int s8 = 0; s8 < 8; ++s8) {
-            const int s = half * 8 + s8;
-            const uint32_t b_off = (uint32_t)((s >> 2) * (PF_D * 128) + (s & 3) * 32);
-            umma_ts(tmem + WS_COL_D2 + 64 * a, tmem + (uint32_t)(16 * s) + a_sel, umma_desc(b_base + b_off), idesc2, 1u);
+        for (int t = 0; t < 3; ++t) {
+          if (t < n_terms) {
+            const u64 db = (t == 2) ? dW2l : dW2h;
+            const uint32_t a_sel = (t == 1) ? 8u : 0u;
+#pragma unroll
+            for (int s8 = 0; s8 < 8; ++s8) {
+              const int s = half * 8 + s8;
+              umma_ts(dcol, tmem + (uint32_t)(16 * s) + a_sel, db + (u64)((s >> 2) * 512 + (s & 3) * 2), idesc2, 1u);
+            }
           }
         }
       };
-      ok = mbar_wait(BAR(0), 0) && ok;  // A1[0] + D2[0] seeded
+      WAIT(0, BAR(0), 0);  // A1[0] + D2[0] seeded
       tc_fence_after();
-      issue_g1(0, 0); tc_commit(BAR(6));
-      issue_g1(0, 1); tc_commit(BAR(7)); tc_commit(BAR(2));
+      if (elect_one()) {
+        issue_g1(0, 0); tc_commit(BAR(7));
+        issue_g1(0, 1); tc_commit(BAR(8)); tc_commit(BAR(2));
+      }
+      __syncwarp();
       for (int it = 0; it < n_my; ++it) {
         const int a = it & 1, an = a ^ 1;
         const uint32_t ph = (uint32_t)(it & 1);
         const bool has_next = it + 1 < n_my;
-        ok = mbar_wait(BAR(8), ph) && ok;   // H half a ready
+        const int d = it % 3;
+        WAIT(1, BAR(9), ph);   // H half a ready
         tc_fence_after();
-        issue_g2(a, 0);
-        if (has_next) {
-          ok = mbar_wait(BAR(0 + an), (uint32_t)(((it + 1) >> 1) & 1)) && ok;
-          tc_fence_after();
-          issue_g1(an, 0); tc_commit(BAR(6));
+        {
+          const long long t0 = TIC();
+          if (elect_one()) {
+            issue_g2(d, 0);
+          }
+          __syncwarp();
+          TOC(4, t0);
         }
-        ok = mbar_wait(BAR(9), ph) && ok;   // H half b ready
-        tc_fence_after();
-        issue_g2(a, 1); tc_commit(BAR(10 + a));
         if (has_next) {
-          issue_g1(an, 1); tc_commit(BAR(7)); tc_commit(BAR(2 + an));
+          WAIT(0, BAR(0 + an), (uint32_t)(((it + 1) >> 1) & 1));
+          tc_fence_after();
+          const long long t0 = TIC();
+          if (elect_one()) { issue_g1(an, 0); tc_commit(BAR(7)); }
+          __syncwarp();
+          TOC(3, t0);
+        }
+        WAIT(2, BAR(10), ph);  // H half b ready
+        tc_fence_after();
+        {
+          const long long t0 = TIC();
+          if (elect_one()) {
+            issue_g2(d, 1); tc_commit(BAR(11 + d));
+            if (has_next) { issue_g1(an, 1); tc_commit(BAR(8)); tc_commit(BAR(2 + an)); }
+          }
+          __syncwarp();
+          TOC(3, t0);
         }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp < 8) {
     // =============================== EPILOGUE ===============================================
-    const int q = warp & 3, chf = (warp - 8) >> 2;   // TMEM lane quadrant, column half
+    const int q = warp & 3, chf = warp >> 2;          // TMEM lane quadrant, column half
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int r = q * 32 + lane, g = r >> 4, s = r & 15;
     auto e1 = [&](int half, bool dump_this) {  // D1[half] cols [64 chf, +64) -> gelu -> bf16 hi/lo in place
       const int c0 = half * 128 + chf * 64;              // TMEM column == hidden unit
       uint32_t v[2][16];
       tmem_ld16(tmem + lane_base + c0, v[0]);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int cc = c0 + c * 16;
+      auto chunk = [&](const uint32_t(&vc)[16], int cc) {
         float bias[16];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float4 bb = *reinterpret_cast<const float4*>(sb1 + cc + 4 * i);
           bias[4 * i] = bb.x; bias[4 * i + 1] = bb.y; bias[4 * i + 2] = bb.z; bias[4 * i + 3] = bb.w;
         }
-        tc_wait_ld();
-        if (c < 3) tmem_ld16(tmem + lane_base + cc + 16, v[(c + 1) & 1]);   // prefetch the next 16 columns
-        const uint32_t(&vc)[16] = v[c & 1];
         if (dump_this) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) dump[r * 320 + cc + i] = __uint_as_float(vc[i]);
@@ -364,19 +417,35 @@ k_colapply_ffn_ws(const PfAttnW* __restrict__ Wc, const PfFfnTcW* __restrict__ W
                  hi[i], lo[i]);
         tmem_st8(tmem + lane_base + cc, hi);
         tmem_st8(tmem + lane_base + cc + 8, lo);
+      };
+#pragma unroll 1
+      for (int c = 0; c < 4; c += 2) {  // ping-pong: the next 16 columns are in flight while these are processed
+        const int cc = c0 + c * 16;
+        long long t0 = TIC();
+        tc_wait_ld();
+        TOC(3, t0);
+        tmem_ld16(tmem + lane_base + cc + 16, v[1]);
+        chunk(v[0], cc);
+        t0 = TIC();
+        tc_wait_ld();
+        TOC(3, t0);
+        if (c + 2 < 4) tmem_ld16(tmem + lane_base + cc + 32, v[0]);
+        chunk(v[1], cc + 16);
       }
+      const long long t1 = TIC();
       tc_wait_st();
+      TOC(4, t1);
       tc_fence_before();
     };
-    auto e2 = [&](int it) {  // D2[it&1] cols [32 chf, +32) -> HBM
-      const int a = it & 1;
-      ok = mbar_wait(BAR(10 + a), (uint32_t)((it >> 1) & 1)) && ok;
+    auto e2 = [&](int it) {  // D2[it%3] cols [32 chf, +32) -> HBM
+      const int a = it % 3;
+      WAIT(2, BAR(11 + a), (uint32_t)((it / 3) & 1));
       tc_fence_after();
       int b, w, pg;
       tm.decode(t_begin + it, b, w, pg);
       const int pair = pg * WS_G + g, site = w * WS_S + s;
       const bool valid = (pair < Pl) && (site < L);
-      float4* dst = reinterpret_cast<float4*>(x + (((size_t)b * Pl + (valid ? pair : 0)) * L + (valid ? site : 0)) * PF_D) + 8 * chf;
+      float* dst = x + (((size_t)b * Pl + (valid ? pair : 0)) * L + (valid ? site : 0)) * PF_D + 32 * chf;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t v[16];
@@ -387,10 +456,8 @@ k_colapply_ffn_ws(const PfAttnW* __restrict__ Wc, const PfFfnTcW* __restrict__ W
           for (int i = 0; i < 16; ++i) dump[r * 320 + 256 + 32 * chf + 16 * c + i] = __uint_as_float(v[i]);
         }
         if (valid) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            dst[4 * c + i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                         __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+          stg256(dst + 16 * c, v);
+          stg256(dst + 16 * c + 8, v + 8);
         }
       }
       tc_fence_before();
@@ -399,35 +466,50 @@ k_colapply_ffn_ws(const PfAttnW* __restrict__ Wc, const PfFfnTcW* __restrict__ W
     for (int it = 0; it < n_my; ++it) {
       const uint32_t ph = (uint32_t)(it & 1);
       const bool dump_this = (dump != nullptr) && blockIdx.x == 0 && it == 0;
-      ok = mbar_wait(BAR(6), ph) && ok;
+      WAIT(0, BAR(7), ph);
       tc_fence_after();
       e1(0, dump_this);
-      mbar_arrive(BAR(8));
-      if (it > 0) e2(it - 1);
-      ok = mbar_wait(BAR(7), ph) && ok;
+      mbar_arrive(BAR(9));
+      {
+        const long long t0 = TIC();
+        if (it > 0) e2(it - 1);
+        TOC(5, t0);
+      }
+      WAIT(1, BAR(8), ph);
       tc_fence_after();
       e1(1, dump_this);
-      mbar_arrive(BAR(9));
+      mbar_arrive(BAR(10));
     }
     if (n_my > 0) e2(n_my - 1);
+  }
+  if (PROF && dump != nullptr && (tid == 256 || tid == 384 || tid == 0)) {
+    // dump[cta][role 0..2][0..3]: total cycles, wait slot 0, 1, 2   (role 0 producer, 1 mma, 2 epilogue)
+    float* o = dump + 128 * 320 + (blockIdx.x * 3 + (tid == 256 ? 0 : tid == 384 ? 1 : 2)) * 8;
+    o[0] = (float)(clock64() - t_start);
+    for (int k = 0; k < 7; ++k) o[1 + k] = (float)tw[k];
   }
   if (!ok && err_flag != nullptr) *err_flag = 2;
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 12) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }
 }
 
 inline int pf_ffn_ws_init() {
-  return (int)cudaFuncSetAttribute(k_colapply_ffn_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
+  int rc = (int)cudaFuncSetAttribute(k_colapply_ffn_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
+  if (rc == 0) rc = (int)cudaFuncSetAttribute(k_colapply_ffn_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
+  return rc;
 }
 
-inline int pf_ffn_ws_launch(const PfAttnW* Wc, const PfFfnTcW* Wt, float* x, const float* colM, int L, int Pl, int B,
-                            int n_sm, int n_terms, int* err_flag, float* dump, cudaStream_t st) {
+inline int pf_ffn_ws_launch(const PfFfnConst& kc, const PfFfnTcW* Wt, float* x, const float* colM, int L, int Pl, int B,
+                            int n_sm, int n_terms, int* err_flag, float* dump, int prof, cudaStream_t st) {
   const long long nt = (long long)B * ((L + WS_S - 1) / WS_S) * ((Pl + WS_G - 1) / WS_G);
   const int grid = (int)(nt < n_sm ? nt : n_sm);
-  k_colapply_ffn_ws<<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(Wc, Wt, x, colM, L, Pl, B, n_terms, err_flag, dump);
+  if (prof)
+    k_colapply_ffn_ws<true><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(kc, Wt, x, colM, L, Pl, B, n_terms, err_flag, dump);
+  else
+    k_colapply_ffn_ws<false><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(kc, Wt, x, colM, L, Pl, B, n_terms, err_flag, dump);
   return (int)cudaGetLastError();
 }
