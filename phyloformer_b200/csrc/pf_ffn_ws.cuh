@@ -51,12 +51,7 @@ struct PfFfnConst {
   float bq[PF_H];        // folded q bias
 };
 
-typedef unsigned long long u64;
-__device__ __forceinline__ u64 pk2(float a, float b) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ void up2(u64 v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+typedef pf_u64 u64;  // packed fp32 pair helpers (pk2, up2, fma2, mul2, add2) live in pf_common.cuh
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -244,7 +239,7 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
             else if (k == 2) q2 = fmaf(d, d, q2); else q3 = fmaf(d, d, q3);
           }
         }
-        rstd = 1.0f / sqrtf(fmaf((q0 + q1) + (q2 + q3), 1.0f / PF_D, 1e-5f));
+        rstd = rsqrt_nr(fmaf((q0 + q1) + (q2 + q3), 1.0f / PF_D, 1e-5f));
         if (PROF) { if (rstd > -1.f) TOC(2, tp0); }
         const float4 qi = *reinterpret_cast<const float4*>(mrow + 256);
         qh[0] = phi_elu1(fmaf(rstd, d0, kc.bq[0])) * qi.x;
@@ -283,7 +278,7 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
           const float d0 = xr[c] - mean, d1 = xr[c + 1] - mean, d2 = xr[c + 2] - mean, d3 = xr[c + 3] - mean;
           q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
         }
-        rstd = 1.0f / sqrtf(fmaf((q0 + q1) + (q2 + q3), 1.0f / PF_D, 1e-5f));
+        rstd = rsqrt_nr(fmaf((q0 + q1) + (q2 + q3), 1.0f / PF_D, 1e-5f));
       }
       {
         unsigned char* a1hi = sm + WS_OFF_A1 + a * 32768;
