@@ -313,10 +313,18 @@ def run_native(args):
         issued = 3.0 if args.precision == "bf16x3" else 1.0
         tf = local_tokens * FLOP_PER_TOKEN_FFN / (ffn_avg * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
-        roofline = {"kernel": "k_colapply_ffn_tc", "bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s",
+        roofline = {"kernel": "k_colapply_ffn_ws" if os.environ.get("PF_FFN_IMPL", "ws") != "tc" else "k_colapply_ffn_tc", "bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s",
                     "frac": tf / peak, "traffic": None, "achieved_issued": tf * issued, "frac_issued": tf * issued / peak,
                     "hbm_gbs": local_tokens * BYTES_PER_TOKEN_FFN / (ffn_avg * 1e-3) / 1e9,
                     "note": f"useful FLOPs = 65536/token; {int(issued)} bf16 MMA passes issued per product"}
+    # DRAM traffic of the dominant kernel from the committed ncu capture (same workload, 1 GPU)
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if tr["workload"] == args.workload and world == tr["n_gpus"] and args.precision != "fp32":
+            roofline["traffic"] = tr["dram_bytes_per_launch"]["k_colapply_ffn_ws"]
+            roofline["traffic_algorithmic"] = tr["algorithmic_bytes_per_launch"]["k_colapply_ffn_ws"]
+    except Exception:  # noqa: BLE001
+        pass
     roofline.update({"peak_source": peaks["source"] + " (sustained)" if roofline["bound"] == "tensor" else peaks["source"],
                      "avg_launch_ms": ffn_avg, "share_of_step": share, "kernels": kernels,
                      "forward_hbm_frac_at_3072B": value * BYTES_PER_TOKEN_FORWARD / 1e9 / peaks["hbm_gbs"] / world})

@@ -8,7 +8,7 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint8, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpf_sm100.so")
+LIB_PATH = os.environ.get("PF_LIB", os.path.join(HERE, "libpf_sm100.so"))  # PF_LIB: A/B-test another build
 
 PF_ABI_VERSION = 1
 PF_PREC_FP32, PF_PREC_BF16X3, PF_PREC_BF16 = 0, 1, 2

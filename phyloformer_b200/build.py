@@ -32,22 +32,23 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
-    """Compile csrc/*.cu for sm_100a into phyloformer_b200/libpf_sm100.so."""
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile csrc/*.cu for sm_100a into phyloformer_b200/libpf_sm100.so (or `out`, with extra -D
+    `defines`, for A/B experiments: load it with PF_LIB=<path>)."""
+    if out is None and not force and not needs_build():
         return LIB
     cmd = [
         _nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
         "-Xptxas", "-v" if verbose else "-O3", "--shared", "-Xcompiler", "-fPIC,-O2",
-        "-o", LIB,
-    ] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart"]
+        "-o", out or LIB,
+    ] + ["-D" + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc failed building libpf_sm100.so")
     if verbose:
         sys.stderr.write(r.stdout + r.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

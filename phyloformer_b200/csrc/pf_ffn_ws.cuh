@@ -239,7 +239,7 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
             else if (k == 2) q2 = fmaf(d, d, q2); else q3 = fmaf(d, d, q3);
           }
         }
-        rstd = rsqrt_nr(fmaf((q0 + q1) + (q2 + q3), 1.0f / PF_D, 1e-5f));
+        rstd = 1.0f / sqrtf(fmaf((q0 + q1) + (q2 + q3), 1.0f / PF_D, 1e-5f));
         if (PROF) { if (rstd > -1.f) TOC(2, tp0); }
         const float4 qi = *reinterpret_cast<const float4*>(mrow + 256);
         qh[0] = phi_elu1(fmaf(rstd, d0, kc.bq[0])) * qi.x;
@@ -278,7 +278,7 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
           const float d0 = xr[c] - mean, d1 = xr[c + 1] - mean, d2 = xr[c + 2] - mean, d3 = xr[c + 3] - mean;
           q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
         }
-        rstd = rsqrt_nr(fmaf((q0 + q1) + (q2 + q3), 1.0f / PF_D, 1e-5f));
+        rstd = 1.0f / sqrtf(fmaf((q0 + q1) + (q2 + q3), 1.0f / PF_D, 1e-5f));
       }
       {
         unsigned char* a1hi = sm + WS_OFF_A1 + a * 32768;

@@ -171,7 +171,7 @@ k_row_attn(const PfAttnW* __restrict__ W, const PfHeadW* __restrict__ hw, float*
       }
     }
     float nv[8];
-    ln_normalize(xc, nv);
+    ln_normalize<true>(xc, nv);
     float part[8];
 #pragma unroll
     for (int v = 0; v < 8; ++v) {

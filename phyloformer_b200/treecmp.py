@@ -1,0 +1,87 @@
+"""Minimal Newick reader and bipartition (Robinson-Foulds) comparison for the topology gate.
+
+Only what the FastME output needs: nested parentheses, leaf names, optional branch lengths and
+internal support labels.  Trees are treated as unrooted."""
+from typing import FrozenSet, List, Optional, Set, Tuple
+
+
+class _Node:
+    __slots__ = ("children", "name", "length")
+
+    def __init__(self):
+        self.children: List["_Node"] = []
+        self.name: Optional[str] = None
+        self.length: Optional[float] = None
+
+
+def parse_newick(text: str) -> _Node:
+    s = text.strip()
+    if s.endswith(";"):
+        s = s[:-1]
+    pos = 0
+
+    def parse() -> _Node:
+        nonlocal pos
+        node = _Node()
+        if s[pos] == "(":
+            pos += 1
+            while True:
+                node.children.append(parse())
+                if s[pos] == ",":
+                    pos += 1
+                    continue
+                if s[pos] == ")":
+                    pos += 1
+                    break
+                raise ValueError(f"bad newick at {pos}: {s[pos:pos + 20]!r}")
+        start = pos
+        while pos < len(s) and s[pos] not in ",():;":
+            pos += 1
+        label = s[start:pos].strip()
+        if label and not node.children:
+            node.name = label
+        if pos < len(s) and s[pos] == ":":
+            pos += 1
+            start = pos
+            while pos < len(s) and s[pos] not in ",()":
+                pos += 1
+            node.length = float(s[start:pos])
+        return node
+
+    return parse()
+
+
+def bipartitions(text: str, min_length: Optional[float] = None) -> Tuple[Set[FrozenSet[str]], Set[str]]:
+    """Non-trivial splits of the unrooted tree, each normalised to the side not containing the
+    alphabetically first leaf.  Internal branches with length <= min_length are collapsed."""
+    root = parse_newick(text)
+    leaves: Set[str] = set()
+    splits: Set[FrozenSet[str]] = set()
+
+    def walk(node: _Node) -> FrozenSet[str]:
+        if not node.children:
+            leaves.add(node.name)
+            return frozenset([node.name])
+        below = frozenset().union(*[walk(c) for c in node.children])
+        if node is not root:
+            if min_length is None or node.length is None or node.length > min_length:
+                splits.add(below)
+        return below
+
+    walk(root)
+    ref = min(leaves)
+    out = set()
+    for sp in splits:
+        side = sp if ref not in sp else frozenset(leaves - sp)
+        if 1 < len(side) < len(leaves) - 1:
+            out.add(side)
+    return out, leaves
+
+
+def rf_distance(a: str, b: str, min_length: Optional[float] = None) -> int:
+    """Robinson-Foulds distance (number of splits in exactly one tree)."""
+    sa, la = bipartitions(a, min_length)
+    sb, lb = bipartitions(b, min_length)
+    if la != lb:
+        raise ValueError("trees have different leaf sets")
+    return len(sa ^ sb)
