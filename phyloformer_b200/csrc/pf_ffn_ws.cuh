@@ -4,13 +4,13 @@
 //
 // Same math and the same UMMA operand images as pf_ffn_tc.cuh; what changes is who does what:
 //
-//   warps 8-11  PRODUCER  one thread per token row (row r <-> TMEM lane r).  Loads the row
+//   warps EW..EW+3   PRODUCER  one thread per token row (row r <-> TMEM lane r).  Loads the row
 //               (16 x LDG.128), applies column attention with the per-site M_l window held in
 //               shared memory, writes x2 + b2 straight into the GEMM2 accumulator in TMEM (the
 //               residual add is then free: GEMM2 accumulates on top of it), LayerNorms, splits
 //               into bf16 hi/lo and stores the GEMM1 A operand (SWIZZLE_128B) in shared memory.
-//   warp  12    MMA       one elected thread issues every tcgen05.mma / tcgen05.commit.
-//   warps 0-7   EPILOGUE  GELU on the GEMM1 accumulator in TMEM, rewritten in place as packed bf16
+//   warp  EW+4       MMA       one elected thread issues every tcgen05.mma / tcgen05.commit.
+//   warps 0..EW-1    EPILOGUE (EW = 8 or 16)  GELU on the GEMM1 accumulator in TMEM, rewritten in place as packed bf16
 //               hi/lo (FFMA2/FMUL2 packed-fp32 math); final rows TMEM -> HBM.
 //
 // A tile is 8 pairs x 16 consecutive sites (128 rows) so that the 16-site window of M_l
@@ -25,7 +25,18 @@
 #pragma once
 #include "pf_ffn_tc.cuh"
 
-#define WS_THREADS 512
+// WS_EW = number of epilogue warps: 8 (512 threads, 128 registers each) or 16 (768 threads launched
+// at 80 registers; setmaxnreg then gives the producer warpgroup 136 and shrinks the MMA warpgroup
+// to 24 (the CTA pool is 768 x 80: 16x32x80 + 4x32x136 + 4x32x24) -- more epilogue warps to hide MUFU/LDS/dependency latency).
+#ifndef WS_EW
+#define WS_EW 8
+#endif
+#define WS_NCG (WS_EW / 4)            // epilogue column groups per TMEM lane quadrant
+#define WS_ECOLS (128 / WS_NCG)       // D1 columns per epilogue warp and half (64 or 32)
+#define WS_E2COLS (64 / WS_NCG)       // D2 columns per epilogue warp (32 or 16)
+#define WS_PW0 WS_EW                  // first producer warp
+#define WS_MW (WS_EW + 4)             // MMA warp
+#define WS_THREADS ((WS_EW + 8) * 32)
 #define WS_G 8    // pairs per tile
 #define WS_S 16   // sites per tile
 #define WS_OFF_A1 131072            // 2 slots x (hi 16 KB + lo 16 KB)
@@ -107,11 +118,11 @@ __device__ __forceinline__ void split2(u64 g, uint32_t& hi, uint32_t& lo) {
 
 struct WsTileMap {  // tile index -> rows
   int L, Pl, nW, nPG;
-  __device__ __forceinline__ void decode(long long t, int& b, int& w, int& pg) const {
-    pg = (int)(t % nPG);
-    const long long bw = t / nPG;
-    w = (int)(bw % nW);
-    b = (int)(bw / nW);
+  __device__ __forceinline__ void decode(unsigned t, int& b, int& w, int& pg) const {  // 32-bit: no emulated 64-bit division
+    const unsigned bw = t / (unsigned)nPG;
+    pg = (int)(t - bw * (unsigned)nPG);
+    b = (int)(bw / (unsigned)nW);
+    w = (int)(bw - (unsigned)b * (unsigned)nW);
   }
 };
 
@@ -143,13 +154,13 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
   if (tid == 0) {
     mbar_init(BAR(0), 128); mbar_init(BAR(1), 128);
     mbar_init(BAR(2), 1);   mbar_init(BAR(3), 1);
-    mbar_init(BAR(4), 256); mbar_init(BAR(5), 256); mbar_init(BAR(6), 256);
+    mbar_init(BAR(4), WS_EW * 32); mbar_init(BAR(5), WS_EW * 32); mbar_init(BAR(6), WS_EW * 32);
     mbar_init(BAR(7), 1);   mbar_init(BAR(8), 1);
-    mbar_init(BAR(9), 256); mbar_init(BAR(10), 256);
+    mbar_init(BAR(9), WS_EW * 32); mbar_init(BAR(10), WS_EW * 32);
     mbar_init(BAR(11), 1);  mbar_init(BAR(12), 1);  mbar_init(BAR(13), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 12) {
+  if (warp == WS_MW) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + WS_OFF_TMEM), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -181,18 +192,22 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
     }
   };
 
-  if (warp >= 8 && warp < 12) {
+  if (warp >= WS_PW0 && warp < WS_MW) {
+#if WS_EW == 16
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");   // producer warpgroup takes the registers the MMA group returns
+#endif
     // =============================== PRODUCER ===============================================
-    const int ptid = tid - 256;        // 0..127
+    const int ptid = tid - WS_PW0 * 32;  // 0..127
     const int r = ptid;                // row == TMEM lane
     const int g = r >> 4, s = r & 15;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     int cur_b = -1, cur_w = -1;
+    int b, w, pg;
+    tm.decode((unsigned)t_begin, b, w, pg);
     for (int it = 0; it < n_my; ++it) {
       const int a = it & 1;
       const uint32_t par = (uint32_t)((it >> 1) & 1);
-      int b, w, pg;
-      tm.decode(t_begin + it, b, w, pg);
+      if (it > 0 && ++pg == tm.nPG) { pg = 0; if (++w == tm.nW) { w = 0; ++b; } }   // next tile, no division
       // ---- row load first: the latency overlaps the waits below ----
       const int pair = pg * WS_G + g, site = w * WS_S + s;
       const bool valid = (pair < Pl) && (site < L);
@@ -303,7 +318,11 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
       tc_fence_before();
       mbar_arrive(BAR(0 + a));
     }
-  } else if (warp == 12) {
+  } else if (warp >= WS_MW) {
+#if WS_EW == 16
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");   // whole MMA warpgroup (issuer + 3 idle warps)
+#endif
+    if (warp == WS_MW) {
     // =============================== MMA ISSUER =============================================
     // The whole warp walks the loop (so descriptors live in uniform registers); one elected lane
     // issues.  Descriptors are built once: per k-step only the 16-byte-unit address field moves.
@@ -385,36 +404,32 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
         }
       }
     }
-  } else if (warp < 8) {
+    }
+  } else if (warp < WS_EW) {
     // =============================== EPILOGUE ===============================================
-    const int q = warp & 3, chf = warp >> 2;          // TMEM lane quadrant, column half
+    const int q = warp & 3, chf = warp >> 2;          // TMEM lane quadrant, column group
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int r = q * 32 + lane, g = r >> 4, s = r & 15;
     auto e1 = [&](int half, bool dump_this) {  // D1[half] cols [64 chf, +64) -> gelu -> bf16 hi/lo in place
-      const int c0 = half * 128 + chf * 64;              // TMEM column == hidden unit
+      const int c0 = half * 128 + chf * WS_ECOLS;        // TMEM column == hidden unit
       uint32_t v[2][16];
       tmem_ld16(tmem + lane_base + c0, v[0]);
       auto chunk = [&](const uint32_t(&vc)[16], int cc) {
-        float bias[16];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 bb = *reinterpret_cast<const float4*>(sb1 + cc + 4 * i);
-          bias[4 * i] = bb.x; bias[4 * i + 1] = bb.y; bias[4 * i + 2] = bb.z; bias[4 * i + 3] = bb.w;
-        }
         if (dump_this) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) dump[r * 320 + cc + i] = __uint_as_float(vc[i]);
         }
         uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          split2(gelu_fast2(__uint_as_float(vc[2 * i]) + bias[2 * i], __uint_as_float(vc[2 * i + 1]) + bias[2 * i + 1]),
-                 hi[i], lo[i]);
+        for (int i = 0; i < 8; ++i) {
+          const float2 bb = *reinterpret_cast<const float2*>(sb1 + cc + 2 * i);
+          split2(gelu_fast2(__uint_as_float(vc[2 * i]) + bb.x, __uint_as_float(vc[2 * i + 1]) + bb.y), hi[i], lo[i]);
+        }
         tmem_st8(tmem + lane_base + cc, hi);
         tmem_st8(tmem + lane_base + cc + 8, lo);
       };
 #pragma unroll 1
-      for (int c = 0; c < 4; c += 2) {  // ping-pong: the next 16 columns are in flight while these are processed
+      for (int c = 0; c < WS_ECOLS / 16; c += 2) {  // ping-pong: the next 16 columns are in flight while these are processed
         const int cc = c0 + c * 16;
         long long t0 = TIC();
         tc_wait_ld();
@@ -424,7 +439,7 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
         t0 = TIC();
         tc_wait_ld();
         TOC(3, t0);
-        if (c + 2 < 4) tmem_ld16(tmem + lane_base + cc + 32, v[0]);
+        if (c + 2 < WS_ECOLS / 16) tmem_ld16(tmem + lane_base + cc + 32, v[0]);
         chunk(v[1], cc + 16);
       }
       const long long t1 = TIC();
@@ -432,23 +447,29 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
       TOC(4, t1);
       tc_fence_before();
     };
-    auto e2 = [&](int it) {  // D2[it%3] cols [32 chf, +32) -> HBM
-      const int a = it % 3;
-      WAIT(2, BAR(11 + a), (uint32_t)((it / 3) & 1));
+    bool first_e2 = true;
+    int eb, ew, epg;                       // tile coordinates of the next tile e2 will store
+    tm.decode((unsigned)t_begin, eb, ew, epg);
+    int slot3 = 0;                         // it % 3 of that tile
+    uint32_t par3 = 0;                     // (it / 3) & 1
+    auto e2 = [&]() {  // D2[slot3] cols [WS_E2COLS chf, +WS_E2COLS) -> HBM, tiles in order
+      const int a = slot3;
+      WAIT(2, BAR(11 + a), par3);
       tc_fence_after();
-      int b, w, pg;
-      tm.decode(t_begin + it, b, w, pg);
+      const int b = eb, w = ew, pg = epg;
+      if (++epg == tm.nPG) { epg = 0; if (++ew == tm.nW) { ew = 0; ++eb; } }
+      if (++slot3 == 3) { slot3 = 0; par3 ^= 1; }
       const int pair = pg * WS_G + g, site = w * WS_S + s;
       const bool valid = (pair < Pl) && (site < L);
-      float* dst = x + (((size_t)b * Pl + (valid ? pair : 0)) * L + (valid ? site : 0)) * PF_D + 32 * chf;
+      float* dst = x + (((size_t)b * Pl + (valid ? pair : 0)) * L + (valid ? site : 0)) * PF_D + WS_E2COLS * chf;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < WS_E2COLS / 16; ++c) {
         uint32_t v[16];
-        tmem_ld16(tmem + lane_base + WS_COL_D2 + 64 * a + 32 * chf + 16 * c, v);
+        tmem_ld16(tmem + lane_base + WS_COL_D2 + 64 * a + WS_E2COLS * chf + 16 * c, v);
         tc_wait_ld();
-        if (dump != nullptr && blockIdx.x == 0 && it == 0) {
+        if (dump != nullptr && blockIdx.x == 0 && first_e2) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) dump[r * 320 + 256 + 32 * chf + 16 * c + i] = __uint_as_float(v[i]);
+          for (int i = 0; i < 16; ++i) dump[r * 320 + 256 + WS_E2COLS * chf + 16 * c + i] = __uint_as_float(v[i]);
         }
         if (valid) {
           stg256(dst + 16 * c, v);
@@ -457,6 +478,7 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
       }
       tc_fence_before();
       mbar_arrive(BAR(4 + a));
+      first_e2 = false;
     };
     for (int it = 0; it < n_my; ++it) {
       const uint32_t ph = (uint32_t)(it & 1);
@@ -467,7 +489,7 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
       mbar_arrive(BAR(9));
       {
         const long long t0 = TIC();
-        if (it > 0) e2(it - 1);
+        if (it > 0) e2();
         TOC(5, t0);
       }
       WAIT(1, BAR(8), ph);
@@ -475,11 +497,11 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
       e1(1, dump_this);
       mbar_arrive(BAR(10));
     }
-    if (n_my > 0) e2(n_my - 1);
+    if (n_my > 0) e2();
   }
-  if (PROF && dump != nullptr && (tid == 256 || tid == 384 || tid == 0)) {
+  if (PROF && dump != nullptr && (tid == WS_PW0 * 32 || tid == WS_MW * 32 || tid == 0)) {
     // dump[cta][role 0..2][0..3]: total cycles, wait slot 0, 1, 2   (role 0 producer, 1 mma, 2 epilogue)
-    float* o = dump + 128 * 320 + (blockIdx.x * 3 + (tid == 256 ? 0 : tid == 384 ? 1 : 2)) * 8;
+    float* o = dump + 128 * 320 + (blockIdx.x * 3 + (tid == WS_PW0 * 32 ? 0 : tid == WS_MW * 32 ? 1 : 2)) * 8;
     o[0] = (float)(clock64() - t_start);
     for (int k = 0; k < 7; ++k) o[1 + k] = (float)tw[k];
   }
@@ -487,7 +509,7 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) {
+  if (warp == WS_MW) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }
 }
@@ -501,6 +523,7 @@ inline int pf_ffn_ws_init() {
 inline int pf_ffn_ws_launch(const PfFfnConst& kc, const PfFfnTcW* Wt, float* x, const float* colM, int L, int Pl, int B,
                             int n_sm, int n_terms, int* err_flag, float* dump, int prof, cudaStream_t st) {
   const long long nt = (long long)B * ((L + WS_S - 1) / WS_S) * ((Pl + WS_G - 1) / WS_G);
+  if (nt > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
   const int grid = (int)(nt < n_sm ? nt : n_sm);
   if (prof)
     k_colapply_ffn_ws<true><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(kc, Wt, x, colM, L, Pl, B, n_terms, err_flag, dump);
