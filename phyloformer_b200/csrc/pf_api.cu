@@ -93,12 +93,21 @@ Plan make_plan(const pf_ctx* h, int B, int n, int L, long long lo, long long hi)
   Plan p;
   p.P = (long long)n * (n - 1) / 2;
   p.Pl = hi - lo;
+  // Column-partial grid: site_tiles x n_chunks x B CTAs, 2 resident per SM.  Pick the chunk count
+  // that minimises (waves x pairs per chunk), i.e. avoids a nearly empty last wave.
   const int site_tiles = (L + 31) / 32;
-  const long long want = (long long)h->n_sm * 4;
-  long long nc = (want + (long long)site_tiles * B - 1) / ((long long)site_tiles * B);
-  if (nc < 1) nc = 1;
-  if (nc > p.Pl) nc = p.Pl > 0 ? p.Pl : 1;
-  p.ppc = (int)((p.Pl + nc - 1) / nc);
+  const long long slots = (long long)h->n_sm * 2;
+  const long long per_chunk = (long long)site_tiles * B;
+  long long best_nc = 1, best_cost = -1;
+  const long long nc_max = p.Pl < 64 ? (p.Pl > 0 ? p.Pl : 1) : 64;
+  for (long long nc = 1; nc <= nc_max; ++nc) {
+    const long long ppc = (p.Pl + nc - 1) / nc;
+    const long long chunks = (p.Pl + ppc - 1) / ppc;
+    const long long waves = (per_chunk * chunks + slots - 1) / slots;
+    const long long cost = waves * ppc * 64 + chunks;  // small penalty on the number of partial buffers
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_nc = nc; }
+  }
+  p.ppc = (int)((p.Pl + best_nc - 1) / best_nc);
   if (p.ppc < 1) p.ppc = 1;
   p.n_chunks = (int)((p.Pl + p.ppc - 1) / p.ppc);
   if (p.n_chunks < 1) p.n_chunks = 1;
