@@ -56,6 +56,7 @@ struct pf_ctx {
   std::vector<PfFfnConst> ffn_const;  // [nb] host copies passed as __grid_constant__ kernel parameters
   int launches = 0;
   int ffn_impl = 1;             // 0: pf_ffn_tc.cuh (phased), 1: pf_ffn_ws.cuh (warp-specialised); env PF_FFN_IMPL=tc|ws
+  int row_impl = 1;             // 0: k_row_attn<0> (register loads), 1: k_row_attn_tma (bulk-copy ring); env PF_ROW_IMPL=ld|tma
   int ws_prof = 0;              // env PF_WS_PROF=1: role timing into the dump buffer (test hook)
   int* err_dev = nullptr;       // set by a kernel whose mbarrier wait timed out
   float* dump_dev = nullptr;    // test hook: raw accumulators of the first FFN tile
@@ -268,7 +269,9 @@ int pf_create(pf_handle* out, const pf_cfg* cfg, const float* const* weights_dev
                                 (int)sizeof(Ffn32Smem)));
   CUDA_TRY(cudaFuncSetAttribute(k_row_attn<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_TRY(cudaFuncSetAttribute(k_row_attn<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(k_row_attn_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   if (const char* e_impl = getenv("PF_FFN_IMPL")) h->ffn_impl = (strcmp(e_impl, "tc") == 0) ? 0 : 1;
+  if (const char* e_row = getenv("PF_ROW_IMPL")) h->row_impl = (strcmp(e_row, "ld") == 0) ? 0 : 1;
   if (const char* e_prof = getenv("PF_WS_PROF")) h->ws_prof = atoi(e_prof);
   int rc = pf_ffn_tc_init();
   if (rc == 0) rc = pf_ffn_ws_init();
@@ -330,6 +333,7 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
   if (ws_bytes < pl.total) return fail(PF_ERR_WORKSPACE, "pf_forward: workspace %zu < %zu bytes", ws_bytes, pl.total);
   if ((long long)B * pl.Pl > 0x7fffffffLL) return fail(PF_ERR_ARG, "pf_forward: too many pair rows");
   const size_t row_smem = sizeof(RowSmem) + (size_t)L * 4 * sizeof(float);
+  if (row_smem + RT_STAGES * RT_STAGE_BYTES > 220 * 1024) h->row_impl = 0;  // very long rows: fall back to register loads
   if (row_smem > 200 * 1024) return fail(PF_ERR_ARG, "pf_forward: L=%d exceeds the row kernel's shared-memory budget", L);
 
   cudaStream_t st = (cudaStream_t)stream;
@@ -374,8 +378,11 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
       if (embed_only) return done();
     } else {
       Timed t_(h, PF_KC_ROW, st);
-      k_row_attn<0><<<rows, 256, row_smem, st>>>(&bw->row, h->head_dev, x, nullptr, nullptr, nullptr, n, L, pair_lo,
-                                                 (int)pl.Pl, 0);
+      if (h->row_impl == 1)
+        k_row_attn_tma<<<rows, 256, row_smem + RT_STAGES * RT_STAGE_BYTES, st>>>(&bw->row, x, L);
+      else
+        k_row_attn<0><<<rows, 256, row_smem, st>>>(&bw->row, h->head_dev, x, nullptr, nullptr, nullptr, n, L, pair_lo,
+                                                   (int)pl.Pl, 0);
     }
     CUDA_TRY(cudaGetLastError());
     stage = 3 * b + 1;

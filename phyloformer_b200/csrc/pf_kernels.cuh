@@ -273,6 +273,221 @@ k_row_attn(const PfAttnW* __restrict__ W, const PfHeadW* __restrict__ hw, float*
 }
 
 // ------------------------------------------------------------------------------------------
+// Row attention, blocks 1..: same math as k_row_attn<0>, but the pair-row is streamed through a
+// shared-memory ring by the TMA engine (cp.async.bulk, 1-D, mbarrier completion): 64-token
+// (16 KB) chunks, 4 stages in flight per CTA, issued by one thread.  The copies use no
+// registers, so memory-level parallelism no longer depends on how many loads each of the 128-
+// register threads can keep in flight.  Both passes over the row (sums, then apply) run through
+// the same ring; the second pass is an L2 hit.
+// ------------------------------------------------------------------------------------------
+#define RT_TOK 64
+#define RT_STAGES 4
+#define RT_STAGE_BYTES (RT_TOK * PF_D * 4)
+
+__device__ __forceinline__ void rt_issue(uint32_t dst, const float* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void rt_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; !ok && spin < (1u << 22); ++spin) {  // bounded: never hang the GPU
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 1000;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(256, 2)
+k_row_attn_tma(const PfAttnW* __restrict__ W, float* __restrict__ x, int L) {
+  extern __shared__ __align__(128) unsigned char smem_rt[];
+  unsigned char* ring = smem_rt;                                               // RT_STAGES x 16 KB
+  RowSmem& sm = *reinterpret_cast<RowSmem*>(smem_rt + RT_STAGES * RT_STAGE_BYTES);
+  float* qcache = reinterpret_cast<float*>(smem_rt + RT_STAGES * RT_STAGE_BYTES + sizeof(RowSmem));  // [L][4]
+  __shared__ __align__(8) unsigned long long bars[RT_STAGES];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j = lane & 7, slot = tid >> 3;
+  float* xrow = x + (size_t)blockIdx.x * L * PF_D;
+  const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
+  const uint32_t bar_u32 = (uint32_t)__cvta_generic_to_shared(bars);
+
+  const int n_chunks = (L + RT_TOK - 1) / RT_TOK;
+  const int n_total = 2 * n_chunks;  // pass A then pass B over the same row
+  auto issue = [&](int c) {          // thread 0 only
+    const int cr = c < n_chunks ? c : c - n_chunks;
+    const int tok0 = cr * RT_TOK;
+    const uint32_t bytes = (uint32_t)(min(RT_TOK, L - tok0) * PF_D * 4);
+    const int st = c % RT_STAGES;
+    rt_issue(ring_u32 + st * RT_STAGE_BYTES, xrow + (size_t)tok0 * PF_D, bytes, bar_u32 + 8 * st);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < RT_STAGES; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_u32 + 8 * s) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int c = 0; c < RT_STAGES && c < n_total; ++c) issue(c);
+  }
+
+  float wqk[8][8];
+#pragma unroll
+  for (int v = 0; v < 8; ++v) {
+    const float4 a = reinterpret_cast<const float4*>(W->wqk[v])[j];
+    const float4 c = reinterpret_cast<const float4*>(W->wqk[v])[8 + j];
+    wqk[v][0] = a.x; wqk[v][1] = a.y; wqk[v][2] = a.z; wqk[v][3] = a.w;
+    wqk[v][4] = c.x; wqk[v][5] = c.y; wqk[v][6] = c.z; wqk[v][7] = c.w;
+  }
+  const float bias_j = W->bqk[j];
+  __syncthreads();  // barriers initialised
+
+  // ---------------- pass A ----------------
+  float S[PF_H][8];
+#pragma unroll
+  for (int h = 0; h < PF_H; ++h)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) S[h][i] = 0.f;
+  float own = 0.f;
+  for (int c = 0; c < n_chunks; ++c) {
+    const int st = c % RT_STAGES;
+    rt_wait(bar_u32 + 8 * st, (uint32_t)((c / RT_STAGES) & 1));
+    const float* stage = reinterpret_cast<const float*>(ring + st * RT_STAGE_BYTES);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int lt = half * 32 + slot;             // token within the chunk
+      const int l = c * RT_TOK + lt;
+      const bool act = l < L;
+      float xc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xc[i] = 0.f;
+      if (act) load_tok(stage + lt * PF_D, j, xc);
+      float nv[8];
+      ln_normalize<true>(xc, nv);
+      float part[8];
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = fmaf(wqk[v][i], nv[i], s);
+        part[v] = s;
+      }
+      const float mine = phi_elu1(grp_reduce8(part, j) + bias_j);
+      float kh[PF_H];
+#pragma unroll
+      for (int h = 0; h < PF_H; ++h) kh[h] = __shfl_sync(PF_FULL, mine, (lane & 24) | h);
+      if (act) {
+        own += mine;
+        if (j >= 4) qcache[(size_t)l * 4 + (j - 4)] = mine;
+#pragma unroll
+        for (int h = 0; h < PF_H; ++h)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) S[h][i] = fmaf(kh[h], nv[i], S[h][i]);
+      }
+    }
+    __syncthreads();  // everyone is done with this stage
+    if (tid == 0 && c + RT_STAGES < n_total) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(c + RT_STAGES);
+    }
+  }
+  // reduce the 4 slots of a warp (fixed tree), then the 8 warps (fixed order)
+#pragma unroll
+  for (int h = 0; h < PF_H; ++h)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = S[h][i];
+      v += __shfl_xor_sync(PF_FULL, v, 8);
+      v += __shfl_xor_sync(PF_FULL, v, 16);
+      S[h][i] = v;
+    }
+  own += __shfl_xor_sync(PF_FULL, own, 8);
+  own += __shfl_xor_sync(PF_FULL, own, 16);
+  if (lane < 8) {
+    sm.red[warp][j] = own;
+#pragma unroll
+    for (int h = 0; h < PF_H; ++h)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sm.red[warp][8 + h * PF_D + chan_of(j, i)] = S[h][i];
+  }
+  __syncthreads();
+  for (int t = tid; t < PF_PART; t += 256) {
+    float s = sm.red[0][t];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) s += sm.red[w][t];
+    sm.tot[t] = s;
+  }
+  __syncthreads();
+  if (tid < PF_D) {
+#pragma unroll
+    for (int h = 0; h < PF_H; ++h)
+      sm.ubar[h][tid] = fmaf(W->gamma[tid], sm.tot[8 + h * PF_D + tid] / sm.tot[h], W->beta[tid]);
+  }
+  __syncthreads();
+  if (tid < PF_D) {
+    const int h = tid >> 4;
+    float acc = W->bv[tid];
+#pragma unroll 8
+    for (int k = 0; k < PF_D; ++k) acc = fmaf(W->wvT[k][tid], sm.ubar[h][k], acc);
+    sm.ctx[tid] = acc;
+  }
+  if (tid < PF_H) sm.qinv[tid] = (float)L / sm.tot[4 + tid];
+  __syncthreads();
+  {
+    const int c = tid >> 2, h = tid & 3;
+    float acc = 0.f;
+#pragma unroll
+    for (int e = 0; e < PF_DH; ++e) acc = fmaf(W->wo[c][h * PF_DH + e], sm.ctx[h * PF_DH + e], acc);
+    sm.M[c][h] = acc;
+  }
+  __syncthreads();
+  // ---------------- pass B: y = x + M qhat + bo ----------------
+  float4 Mr[8];
+  float bo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = chan_of(j, i);
+    Mr[i] = *reinterpret_cast<const float4*>(sm.M[c]);
+    bo[i] = W->bo[c];
+  }
+  const float4 qi = *reinterpret_cast<const float4*>(sm.qinv);
+  for (int c = n_chunks; c < n_total; ++c) {
+    const int st = c % RT_STAGES;
+    rt_wait(bar_u32 + 8 * st, (uint32_t)((c / RT_STAGES) & 1));
+    const float* stage = reinterpret_cast<const float*>(ring + st * RT_STAGE_BYTES);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int lt = half * 32 + slot;
+      const int l = (c - n_chunks) * RT_TOK + lt;
+      if (l < L) {
+        float xc[8];
+        load_tok(stage + lt * PF_D, j, xc);
+        float4 q = *reinterpret_cast<const float4*>(qcache + (size_t)l * 4);
+        q.x *= qi.x; q.y *= qi.y; q.z *= qi.z; q.w *= qi.w;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float a = bo[i];
+          a = fmaf(Mr[i].x, q.x, a);
+          a = fmaf(Mr[i].y, q.y, a);
+          a = fmaf(Mr[i].z, q.z, a);
+          a = fmaf(Mr[i].w, q.w, a);
+          xc[i] += a;
+        }
+        store_tok(xrow + (size_t)l * PF_D, j, xc);
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && c + RT_STAGES < n_total) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(c + RT_STAGES);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Column attention, step 1: partial sums over a chunk of pairs at each site.
 //   part[chunk][b][l][0:4]  = sum_p k~_h      [4:8] = sum_p q~_h      [8+64h+c] = sum_p k~_h n_c
 // (n = LN(x) without affine; k~, q~ un-normalised phi values, attention.py:179-180 with
