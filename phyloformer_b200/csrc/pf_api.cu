@@ -97,7 +97,7 @@ Plan make_plan(const pf_ctx* h, int B, int n, int L, long long lo, long long hi)
   // Column-partial grid: site_tiles x n_chunks x B CTAs, 2 resident per SM.  Pick the chunk count
   // that minimises (waves x pairs per chunk), i.e. avoids a nearly empty last wave.
   const int site_tiles = (L + 31) / 32;
-  const long long slots = (long long)h->n_sm * 2;
+  const long long slots = (long long)h->n_sm * PF_COL_MINB;
   const long long per_chunk = (long long)site_tiles * B;
   long long best_nc = 1, best_cost = -1;
   const long long nc_max = p.Pl < 64 ? (p.Pl > 0 ? p.Pl : 1) : 64;

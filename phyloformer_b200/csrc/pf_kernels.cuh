@@ -494,7 +494,10 @@ k_row_attn_tma(const PfAttnW* __restrict__ W, float* __restrict__ x, int L) {
 //  R=L, N=P).  A token slot owns one site and walks down the pairs, so there is no cross-lane
 //  reduction and the order of the sum is fixed.   grid = (ceil(L/32), n_chunks, B)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2)
+#ifndef PF_COL_MINB
+#define PF_COL_MINB 2
+#endif
+__global__ void __launch_bounds__(256, PF_COL_MINB)
 k_col_partial(const PfAttnW* __restrict__ W, const float* __restrict__ x, float* __restrict__ part,
               int L, int Pl, int pairs_per_chunk) {
   const int tid = threadIdx.x, lane = tid & 31;
