@@ -39,8 +39,10 @@
 #define WS_THREADS ((WS_EW + 8) * 32)
 #define WS_G 8    // pairs per tile
 #define WS_S 16   // sites per tile
-#define WS_OFF_A1 131072            // 2 slots x (hi 16 KB + lo 16 KB)
-#define WS_OFF_MWIN 196608          // [16][260] floats
+#define WS_OFF_A1 131072            // GEMM1 A operand: hi 16 KB + lo 16 KB (single buffer)
+#define WS_XROW 272                 // staged row stride: 256 B + 16 B pad (conflict-free LDS.128 per row)
+#define WS_OFF_XST 163840           // [128] rows prefetched with cp.async one tile ahead
+#define WS_OFF_MWIN 198656          // [16][260] floats
 #define WS_MWIN_BYTES (WS_S * PF_MROW * 4)
 #define WS_OFF_WQ (WS_OFF_MWIN + 16896)   // [64][4] folded column q weights
 #define WS_OFF_BO (WS_OFF_WQ + 1024)      // [64]
@@ -212,23 +214,42 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
     int cur_b = -1, cur_w = -1;
     int b, w, pg;
     tm.decode((unsigned)t_begin, b, w, pg);
+    const uint32_t xst_u32 = sbase + WS_OFF_XST + (uint32_t)r * WS_XROW;
+    auto prefetch_row = [&](size_t tok) {  // 16 x 16-byte cp.async: global row -> this thread's smem row
+      const float* src = x + tok * PF_D;
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(xst_u32 + 16 * c), "l"(src + 4 * c) : "memory");
+    };
+    if (n_my > 0) {
+      const int pair0 = pg * WS_G + g, site0 = w * WS_S + s;
+      if (pair0 < Pl && site0 < L) prefetch_row(((size_t)b * Pl + pair0) * L + site0);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     for (int it = 0; it < n_my; ++it) {
-      const int a = it & 1;
-      const uint32_t par = (uint32_t)((it >> 1) & 1);
+      const uint32_t par = (uint32_t)(it & 1);
       if (it > 0 && ++pg == tm.nPG) { pg = 0; if (++w == tm.nW) { w = 0; ++b; } }   // next tile, no division
-      // ---- row load first: the latency overlaps the waits below ----
+      // ---- this tile's row was prefetched into smem by cp.async one tile ago ----
       const int pair = pg * WS_G + g, site = w * WS_S + s;
       const bool valid = (pair < Pl) && (site < L);
       float xr[PF_D];
       {
-        const float* src = x + (((size_t)b * Pl + (valid ? pair : 0)) * L + (valid ? site : 0)) * PF_D;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        const float4* srow = reinterpret_cast<const float4*>(sm + WS_OFF_XST + r * WS_XROW);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (valid) ldg256(src + 8 * c, v);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) xr[8 * c + i] = v[i];
+        for (int c = 0; c < 16; ++c) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid) v = srow[c];
+          xr[4 * c] = v.x; xr[4 * c + 1] = v.y; xr[4 * c + 2] = v.z; xr[4 * c + 3] = v.w;
         }
+        // prefetch the next tile's row into the same slot (this thread is its only reader)
+        if (it + 1 < n_my) {
+          int nb = b, nw = w, npg = pg + 1;
+          if (npg == tm.nPG) { npg = 0; if (++nw == tm.nW) { nw = 0; ++nb; } }
+          const int npair = npg * WS_G + g, nsite = nw * WS_S + s;
+          if (npair < Pl && nsite < L) prefetch_row(((size_t)nb * Pl + npair) * L + nsite);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
       }
       if (b != cur_b || w != cur_w) {  // new site window: reload M_l (producer warps only)
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -279,7 +300,7 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
       }
       // ---- wait for the slot, then seed the GEMM2 accumulator with x2 + b2 ----
       const int d = it % 3;                        // GEMM2 accumulator slot (3-deep ring)
-      WAIT(0, BAR(2 + a), par ^ 1);   // A1[a] free (G1 of tile it-2 done)
+      WAIT(0, BAR(2), par ^ 1);       // A1 free (both GEMM1 halves of the previous tile done)
       WAIT(1, BAR(4 + d), (uint32_t)(((it / 3) & 1) ^ 1));   // D2[d] free (E2 of tile it-3 done)
       tc_fence_after();
 #pragma unroll
@@ -304,7 +325,7 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
         rstd = 1.0f / sqrtf(fmaf((q0 + q1) + (q2 + q3), 1.0f / PF_D, 1e-5f));
       }
       {
-        unsigned char* a1hi = sm + WS_OFF_A1 + a * 32768;
+        unsigned char* a1hi = sm + WS_OFF_A1;
         unsigned char* a1lo = a1hi + 16384;
         const uint32_t rowoff = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
         const u64 nm = pk2(-mean, -mean), rs = pk2(rstd, rstd);
@@ -324,7 +345,7 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
       { const long long t0 = TIC(); tc_wait_st(); TOC(3, t0); }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(BAR(0 + a));
+      mbar_arrive(BAR(0));
     }
   } else if (warp >= WS_MW) {
 #if WS_EW == 16
@@ -337,11 +358,11 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
     if (n_my > 0) {
       const uint32_t idesc1 = umma_idesc(128, 128), idesc2 = umma_idesc(128, 64);
       const u64 dA00 = umma_desc(sbase + WS_OFF_A1), dA01 = umma_desc(sbase + WS_OFF_A1 + 16384);
-      const u64 dA10 = umma_desc(sbase + WS_OFF_A1 + 32768), dA11 = umma_desc(sbase + WS_OFF_A1 + 49152);
       const u64 dW1h = umma_desc(sbase + TC_OFF_W1HI), dW1l = umma_desc(sbase + TC_OFF_W1LO);
       const u64 dW2h = umma_desc(sbase + TC_OFF_W2HI), dW2l = umma_desc(sbase + TC_OFF_W2LO);
       auto issue_g1 = [&](int a, int half) {  // D1[half] = A1[a] . W1[half*128 .. +128)^T
-        const u64 ah = a ? dA10 : dA00, al = a ? dA11 : dA01;
+        const u64 ah = dA00, al = dA01;
+        (void)a;
         const u64 hoff = (u64)(half * (16384 >> 4));
         const uint32_t dcol = tmem + 128 * half;
 #pragma unroll
@@ -377,7 +398,7 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
       }
       __syncwarp();
       for (int it = 0; it < n_my; ++it) {
-        const int a = it & 1, an = a ^ 1;
+        const int an = 0;
         const uint32_t ph = (uint32_t)(it & 1);
         const bool has_next = it + 1 < n_my;
         const int d = it % 3;
@@ -392,7 +413,7 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
           TOC(4, t0);
         }
         if (has_next) {
-          WAIT(0, BAR(0 + an), (uint32_t)(((it + 1) >> 1) & 1));
+          WAIT(0, BAR(0), (uint32_t)((it + 1) & 1));
           tc_fence_after();
           const long long t0 = TIC();
           if (elect_one()) { issue_g1(an, 0); tc_commit(BAR(7)); }
@@ -405,7 +426,7 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
           const long long t0 = TIC();
           if (elect_one()) {
             issue_g2(d, 1); tc_commit(BAR(11 + d));
-            if (has_next) { issue_g1(an, 1); tc_commit(BAR(8)); tc_commit(BAR(2 + an)); }
+            if (has_next) { issue_g1(an, 1); tc_commit(BAR(8)); tc_commit(BAR(2)); }
           }
           __syncwarp();
           TOC(3, t0);
