@@ -8,9 +8,12 @@ Same command line as the reference's infer_alns.py (infer_alns.py:42-60):
 For every .fa/.fasta file in ALNDIR writes OUTDIR/<stem>.phy (PHYLIP distance matrix,
 '%.10f', same text as the reference's vec_to_phylip) and, with -t, a neighbour-joining tree
 (needs scikit-bio, like the reference).  Differences under the hood: the alignment goes to
-the GPU as (n, L) uint8 residue codes instead of a 22-channel fp32 one-hot, the symmetric
-matrix is assembled on the device, and the text is formatted in one vectorised pass.
-Extra environment knobs: PF_PRECISION=fp32|bf16x3|bf16.
+the GPU as (n, L) uint8 residue codes instead of a 22-channel fp32 one-hot, alignments of the
+same shape are run as one batched forward (the reference loops file by file,
+infer_alns.py:97-112), the symmetric matrix is assembled on the device, the text is formatted
+in one vectorised pass, and -t falls back to a built-in neighbour joining when scikit-bio is
+not installed.  Extra environment knobs: PF_PRECISION=fp32|bf16x3|bf16,
+PF_MAX_BATCH_TOKENS (pair*sites per batched call, default 2e7).
 """
 import argparse
 import os
@@ -73,9 +76,15 @@ def main(argv=None):
     parser.add_argument("--trees", "-t", action="store_true", help="Output NJ trees as well as matrices")
     args = parser.parse_args(argv)
 
+    nj = None
     if args.trees:
-        from skbio import DistanceMatrix
-        from skbio.tree import nj
+        try:
+            from skbio import DistanceMatrix
+            from skbio.tree import nj as sk_nj
+            nj = lambda dm, ids: str(sk_nj(DistanceMatrix(dm, ids=ids)))  # noqa: E731
+        except ImportError:
+            from phyloformer_b200.nj import neighbor_joining
+            nj = lambda dm, ids: neighbor_joining(dm, ids) + "\n"          # noqa: E731
     if not torch.cuda.is_available():
         raise RuntimeError("infer_alns.py (B200 build) needs a CUDA device; there is no CPU fallback")
     if args.outdir is None:
@@ -87,20 +96,34 @@ def main(argv=None):
     out_dir = os.path.abspath(args.outdir)
     os.makedirs(out_dir, exist_ok=True)
 
-    with torch.no_grad():
-        for alnpath in tqdm(sorted(glob(f"{in_dir}/*"))):
-            if not has_fasta_ext(alnpath):
-                raise ValueError("Input files must be fasta files (.fa or .fasta). Got " f"{alnpath}")
-            stem = Path(alnpath).stem
-            idx, ids = load_alignment_idx(alnpath)
-            preds = model.forward_idx(idx.to(device, non_blocking=True))
-            dm, phylip = vec_to_phylip(preds, ids, model)
-            with open(os.path.join(out_dir, f"{stem}.phy"), "w") as outfile:
-                outfile.write(phylip)
-            if args.trees:
-                sk = DistanceMatrix(dm.cpu().numpy().astype(np.float64), ids=ids)
-                with open(os.path.join(out_dir, f"{stem}.nj.nwk"), "w") as outfile:
-                    outfile.write(str(nj(sk)))
+    # parse everything first (host), bucket by alignment shape
+    paths = sorted(glob(f"{in_dir}/*"))
+    for alnpath in paths:
+        if not has_fasta_ext(alnpath):
+            raise ValueError("Input files must be fasta files (.fa or .fasta). Got " f"{alnpath}")
+    buckets = {}
+    for alnpath in paths:
+        idx, ids = load_alignment_idx(alnpath)
+        buckets.setdefault(tuple(idx.shape), []).append((alnpath, idx, ids))
+    max_tokens = float(os.environ.get("PF_MAX_BATCH_TOKENS", 2e7))
+
+    with torch.no_grad(), tqdm(total=len(paths)) as bar:
+        for (n, L), items in buckets.items():
+            per_msa = max(1, n * (n - 1) // 2 * L)
+            step = max(1, int(max_tokens // per_msa))
+            for lo in range(0, len(items), step):
+                chunk = items[lo:lo + step]
+                batch = torch.stack([it[1] for it in chunk]).to(device, non_blocking=True)   # (B,n,L) uint8
+                preds = model.forward_idx(batch, squeeze=False)                              # (B,P)
+                mats = model.distance_matrix(preds, n).cpu().numpy()                         # (B,n,n)
+                for (alnpath, _, ids), dm in zip(chunk, mats):
+                    stem = Path(alnpath).stem
+                    with open(os.path.join(out_dir, f"{stem}.phy"), "w") as outfile:
+                        outfile.write(matrix_to_phylip(dm, ids))
+                    if nj is not None:
+                        with open(os.path.join(out_dir, f"{stem}.nj.nwk"), "w") as outfile:
+                            outfile.write(nj(dm.astype(np.float64), ids))
+                    bar.update(1)
 
 
 if __name__ == "__main__":

@@ -85,3 +85,31 @@ def rf_distance(a: str, b: str, min_length: Optional[float] = None) -> int:
     if la != lb:
         raise ValueError("trees have different leaf sets")
     return len(sa ^ sb)
+
+
+def patristic_distances(text: str):
+    """(leaf names, matrix of path lengths between leaves) of a Newick tree with branch lengths."""
+    import numpy as np
+    root = parse_newick(text)
+    names, paths = [], []  # per leaf: list of (node id, length) up to the root
+
+    def walk(node, trail):
+        here = trail + [(id(node), node.length or 0.0)]
+        if not node.children:
+            names.append(node.name)
+            paths.append(here)
+        for c in node.children:
+            walk(c, here)
+
+    walk(root, [])
+    n = len(names)
+    dm = np.zeros((n, n))
+    for a in range(n):
+        da = {k: i for i, (k, _) in enumerate(paths[a])}
+        for b in range(a + 1, n):
+            # deepest common node
+            common = max(i for i, (k, _) in enumerate(paths[b]) if k in da and da[k] == i and paths[a][i][0] == k)
+            la = sum(l for _, l in paths[a][common + 1:])
+            lb = sum(l for _, l in paths[b][common + 1:])
+            dm[a, b] = dm[b, a] = la + lb
+    return names, dm

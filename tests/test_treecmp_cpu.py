@@ -21,3 +21,18 @@ def test_reference_trees_parse():
         n = int(stem.split("_")[1])
         assert len(leaves) == n and len(splits) <= n - 3
         assert rf_distance(nwk, nwk) == 0
+
+
+def test_neighbor_joining_recovers_additive_trees():
+    """NJ is exact on additive (tree) metrics: feed it the path-length matrices of the stored
+    reference FastME trees and require RF = 0 (ignoring zero-length branches)."""
+    import numpy as np
+    from phyloformer_b200.nj import neighbor_joining
+    from phyloformer_b200.treecmp import patristic_distances
+    trees = json.load(open(os.path.join(GOLDEN, "ref_trees_pf.json")))
+    for stem in ("0_20_tips", "2_30_tips", "2_50_tips"):
+        names, dm = patristic_distances(trees[stem])
+        assert np.allclose(dm, dm.T) and (dm >= 0).all()
+        nwk = neighbor_joining(dm, names)
+        assert rf_distance(nwk, trees[stem], min_length=1e-9) == 0, stem
+    assert neighbor_joining(np.array([[0, 2.0], [2.0, 0]]), ["a", "b"]) == "(a:1.0000000000,b:1.0000000000);"
