@@ -34,8 +34,6 @@
 #define WS_EW 8
 #endif
 #define WS_NCG (WS_EW / 4)            // epilogue column groups per TMEM lane quadrant
-#define WS_ECOLS (128 / WS_NCG)       // D1 columns per epilogue warp and half (64 or 32)
-#define WS_E2COLS (64 / WS_NCG)       // D2 columns per epilogue warp (32 or 16)
 // WS_PSPLIT = 1: every token row is produced by TWO threads (channels 0-31 / 32-63) in two warps of
 // the same TMEM lane quadrant, which exchange their LayerNorm / dot-product partial sums through
 // shared memory: 8 producer warps, half the serial work per thread.
@@ -387,6 +385,8 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
   if (warp >= WS_PW0 && warp < WS_PW0 + WS_NPW) {
 #if WS_EW == 16
     asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");   // producer warpgroup takes the registers the MMA group returns
+#elif WS_EW == 12
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
 #endif
     // =============================== PRODUCER ===============================================
     const int ptid = tid - WS_PW0 * 32;  // 0..127
@@ -534,6 +534,8 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
   if (warp >= WS_MW) {
 #if WS_EW == 16
     asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");   // whole MMA warpgroup (issuer + 3 idle warps)
+#elif WS_EW == 12
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // 640 x 96 = 12x32x96 + 4x32x128 + 4x32x40 + slack
 #endif
     if (warp == WS_MW) {
     // =============================== MMA ISSUER =============================================
@@ -574,47 +576,37 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
           }
         }
       };
-      WAIT(0, BAR(0), 0);  // A1[0] + D2[0] seeded
-      tc_fence_after();
-      if (elect_one()) {
-        issue_g1(0, 0); tc_commit(BAR(7));
-        issue_g1(0, 1); tc_commit(BAR(8)); tc_commit(BAR(2));
-      }
-      __syncwarp();
-      for (int it = 0; it < n_my; ++it) {
-        const int an = 0;
-        const uint32_t ph = (uint32_t)(it & 1);
+      // Rolled step loop (one code instance of each issue function).  Order on the tensor pipe:
+      //   G1a(0) G1b(0) | G2a(i) G1a(i+1) G2b(i) G1b(i+1) ...   (in-order issue covers the WAR on D1)
+#pragma unroll 1
+      for (int step = -1; step < 2 * n_my; ++step) {
+        const int it = step >> 1, half = step & 1;      // step -1: preamble for tile 0 (it = -1, half = 1)
+        const int d = (it < 0 ? 0 : it) % 3;
         const bool has_next = it + 1 < n_my;
-        const int d = it % 3;
-        WAIT(1, BAR(9), ph);   // H half a ready
-        tc_fence_after();
-        {
-          const long long t0 = TIC();
+        const long long t0 = TIC();
+        if (step >= 0) {
+          WAIT(1 + half, BAR(9 + half), (uint32_t)(it & 1));   // H half ready
+          tc_fence_after();
           if (elect_one()) {
-            issue_g2(d, 0);
+            issue_g2(d, half);
+            if (half == 1) tc_commit(BAR(11 + d));
           }
           __syncwarp();
-          TOC(4, t0);
         }
-        if (has_next) {
+        if ((half == 0 && has_next) || step == -1) {   // the next tile's A operand must have landed
           WAIT(0, BAR(0), (uint32_t)((it + 1) & 1));
           tc_fence_after();
-          const long long t0 = TIC();
-          if (elect_one()) { issue_g1(an, 0); tc_commit(BAR(7)); }
-          __syncwarp();
-          TOC(3, t0);
         }
-        WAIT(2, BAR(10), ph);  // H half b ready
-        tc_fence_after();
-        {
-          const long long t0 = TIC();
+        if (has_next) {
           if (elect_one()) {
-            issue_g2(d, 1); tc_commit(BAR(11 + d));
-            if (has_next) { issue_g1(an, 1); tc_commit(BAR(8)); tc_commit(BAR(2)); }
+            if (step == -1) { issue_g1(0, 0); tc_commit(BAR(7)); }
+            issue_g1(0, half);
+            tc_commit(BAR(7 + half));
+            if (half == 1) tc_commit(BAR(2));
           }
-          __syncwarp();
-          TOC(3, t0);
         }
+        __syncwarp();
+        TOC(3, t0);
       }
     }
     }
@@ -623,10 +615,11 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
     const int q = warp & 3, chf = (warp - WS_EW0) >> 2;   // TMEM lane quadrant, column group
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int r = q * 32 + lane, g = r >> 4, s = r & 15;
-    auto e1 = [&](int half, bool dump_this) {  // D1[half] cols [64 chf, +64) -> gelu -> bf16 hi/lo in place
-      const int c0 = half * 128 + chf * WS_ECOLS;        // TMEM column == hidden unit
+    auto e1 = [&](int half, bool dump_this) {  // this warp's 16-column chunks of D1[half] -> gelu -> bf16 hi/lo in place
+      // chunk j of the half (16 hidden units) belongs to column group j % WS_NCG
+      constexpr int NCH = (8 - 1) / WS_NCG + 1;            // max chunks per warp and half
       uint32_t v[2][16];
-      tmem_ld16(tmem + lane_base + c0, v[0]);
+      auto col_of = [&](int i) { return half * 128 + (chf + i * WS_NCG) * 16; };   // TMEM column == hidden unit
       auto chunk = [&](const uint32_t(&vc)[16], int cc) {
         if (dump_this) {
 #pragma unroll
@@ -641,19 +634,24 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
         tmem_st8(tmem + lane_base + cc, hi);
         tmem_st8(tmem + lane_base + cc + 8, lo);
       };
+      const int n_mine = (8 - chf + WS_NCG - 1) / WS_NCG;   // chunks of this warp in a half
+      tmem_ld16(tmem + lane_base + col_of(0), v[0]);
 #pragma unroll 1
-      for (int c = 0; c < WS_ECOLS / 16; c += 2) {  // ping-pong: the next 16 columns are in flight while these are processed
-        const int cc = c0 + c * 16;
-        long long t0 = TIC();
-        tc_wait_ld();
-        TOC(3, t0);
-        tmem_ld16(tmem + lane_base + cc + 16, v[1]);
-        chunk(v[0], cc);
-        t0 = TIC();
-        tc_wait_ld();
-        TOC(3, t0);
-        if (c + 2 < WS_ECOLS / 16) tmem_ld16(tmem + lane_base + cc + 32, v[0]);
-        chunk(v[1], cc + 16);
+      for (int i = 0; i < NCH; i += 2) {  // ping-pong (rolled: keeps the epilogue inside the instruction cache)
+        if (i < n_mine) {
+          const long long t0 = TIC();
+          tc_wait_ld();
+          TOC(3, t0);
+          if (i + 1 < n_mine) tmem_ld16(tmem + lane_base + col_of(i + 1), v[1]);
+          chunk(v[0], col_of(i));
+        }
+        if (i + 1 < n_mine) {
+          const long long t0 = TIC();
+          tc_wait_ld();
+          TOC(3, t0);
+          if (i + 2 < n_mine) tmem_ld16(tmem + lane_base + col_of(i + 2), v[0]);
+          chunk(v[1], col_of(i + 1));
+        }
       }
       const long long t1 = TIC();
       tc_wait_st();
@@ -674,43 +672,49 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
       if (++slot3 == 3) { slot3 = 0; par3 ^= 1; }
       const int pair = pg * WS_G + g, site = w * WS_S + s;
       const bool valid = (pair < Pl) && (site < L);
-      float* dst = x + (((size_t)b * Pl + (valid ? pair : 0)) * L + (valid ? site : 0)) * PF_D + WS_E2COLS * chf;
+      float* dst = x + (((size_t)b * Pl + (valid ? pair : 0)) * L + (valid ? site : 0)) * PF_D;
+      // D2 has four 16-column chunks; chunk j goes to column group (WS_NCG-1-j) mod WS_NCG, which
+      // gives the extra store chunk to the group with the fewest GELU chunks
 #pragma unroll
-      for (int c = 0; c < WS_E2COLS / 16; ++c) {
-        uint32_t v[16];
-        tmem_ld16(tmem + lane_base + WS_COL_D2 + 64 * a + WS_E2COLS * chf + 16 * c, v);
-        tc_wait_ld();
-        if (dump != nullptr && blockIdx.x == 0 && first_e2) {
+      for (int jc = 0; jc < 4; ++jc) {
+        if ((WS_NCG - 1 - jc % WS_NCG) == chf) {
+          uint32_t v[16];
+          tmem_ld16(tmem + lane_base + WS_COL_D2 + 64 * a + 16 * jc, v);
+          tc_wait_ld();
+          if (dump != nullptr && blockIdx.x == 0 && first_e2) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) dump[r * 320 + 256 + WS_E2COLS * chf + 16 * c + i] = __uint_as_float(v[i]);
-        }
-        if (valid) {
-          stg256(dst + 16 * c, v);
-          stg256(dst + 16 * c + 8, v + 8);
+            for (int i = 0; i < 16; ++i) dump[r * 320 + 256 + 16 * jc + i] = __uint_as_float(v[i]);
+          }
+          if (valid) {
+            stg256(dst + 16 * jc, v);
+            stg256(dst + 16 * jc + 8, v + 8);
+          }
         }
       }
       tc_fence_before();
       mbar_arrive(BAR(4 + a));
       first_e2 = false;
     };
-    for (int it = 0; it < n_my; ++it) {
-      const uint32_t ph = (uint32_t)(it & 1);
-      const bool dump_this = (dump != nullptr) && blockIdx.x == 0 && it == 0;
-      WAIT(0, BAR(7), ph);
-      tc_fence_after();
-      e1(0, dump_this);
-      mbar_arrive(BAR(9));
-      {
+    // One code instance of e1 and e2 (rolled loops): the three roles run different code at the
+    // same time and together must stay close to the instruction cache (measured: unrolling e1
+    // 4x costs 17 % of the kernel).  Sequence per tile: E1a(it)  E2(it-1)  E1b(it).
+#pragma unroll 1
+    for (int step = 0; step < 2 * n_my + 1; ++step) {
+      const int it = step >> 1, half = step & 1;
+      if (step < 2 * n_my) {
+        const uint32_t ph = (uint32_t)(it & 1);
+        const bool dump_this = (dump != nullptr) && blockIdx.x == 0 && it == 0;
+        WAIT(half, BAR(7 + half), ph);
+        tc_fence_after();
+        e1(half, dump_this);
+        mbar_arrive(BAR(9 + half));
+      }
+      if (half == 0 && step > 0) {   // after E1a(it): store tile it-1 (also the final tile at step == 2 n_my)
         const long long t0 = TIC();
-        if (it > 0) e2();
+        e2();
         TOC(5, t0);
       }
-      WAIT(1, BAR(8), ph);
-      tc_fence_after();
-      e1(1, dump_this);
-      mbar_arrive(BAR(10));
     }
-    if (n_my > 0) e2();
   }
   if (PROF && dump != nullptr && (tid == WS_PW0 * 32 || tid == WS_MW * 32 || tid == WS_EW0 * 32)) {
     // dump[cta][role 0..2][0..3]: total cycles, wait slot 0, 1, 2   (role 0 producer, 1 mma, 2 epilogue)
