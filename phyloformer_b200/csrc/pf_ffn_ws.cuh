@@ -33,6 +33,12 @@
 #ifndef WS_EW
 #define WS_EW 8
 #endif
+// WS_STORE_WARPS = 1: the final rows (TMEM -> HBM) are stored by the four warps of the MMA warpgroup
+// (the issuer between its issue steps, and its three otherwise idle siblings) instead of the
+// epilogue warps, which are the critical role.
+#ifndef WS_STORE_WARPS
+#define WS_STORE_WARPS 0   // measured: no difference (35.5 ms either way); only valid with WS_EW == 8
+#endif
 #define WS_NCG (WS_EW / 4)            // epilogue column groups per TMEM lane quadrant
 // WS_PSPLIT = 1: every token row is produced by TWO threads (channels 0-31 / 32-63) in two warps of
 // the same TMEM lane quadrant, which exchange their LayerNorm / dot-product partial sums through
@@ -174,7 +180,8 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
   if (tid == 0) {
     mbar_init(BAR(0), WS_NPW * 32); mbar_init(BAR(1), WS_NPW * 32);
     mbar_init(BAR(2), 1);   mbar_init(BAR(3), 1);
-    mbar_init(BAR(4), WS_EW * 32); mbar_init(BAR(5), WS_EW * 32); mbar_init(BAR(6), WS_EW * 32);
+    mbar_init(BAR(4), WS_STORE_WARPS ? 128 : WS_EW * 32); mbar_init(BAR(5), WS_STORE_WARPS ? 128 : WS_EW * 32);
+    mbar_init(BAR(6), WS_STORE_WARPS ? 128 : WS_EW * 32);
     mbar_init(BAR(7), 1);   mbar_init(BAR(8), 1);
     mbar_init(BAR(9), WS_EW * 32); mbar_init(BAR(10), WS_EW * 32);
     mbar_init(BAR(11), 1);  mbar_init(BAR(12), 1);  mbar_init(BAR(13), 1);
@@ -537,6 +544,54 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
 #elif WS_EW == 12
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // 640 x 96 = 12x32x96 + 4x32x128 + 4x32x40 + slack
 #endif
+#if WS_STORE_WARPS
+    // ---- final-row store, one TMEM lane quadrant per warp of this warpgroup ----
+    const int sq = warp & 3;
+    const uint32_t s_lane_base = (uint32_t)(sq * 32) << 16;
+    const int sr = sq * 32 + lane, sg = sr >> 4, ss = sr & 15;
+    int sb_, sw_, spg_;
+    tm.decode((unsigned)t_begin, sb_, sw_, spg_);
+    int s_slot3 = 0;
+    uint32_t s_par3 = 0;
+    bool s_first = true;
+    auto store_tile = [&]() {   // D2[slot] (64 columns) of the next tile in order -> HBM
+      const int a = s_slot3;
+      WAIT(5, BAR(11 + a), s_par3);
+      tc_fence_after();
+      const int pair = spg_ * WS_G + sg, site = sw_ * WS_S + ss;
+      const bool valid = (pair < Pl) && (site < L);
+      float* dst = x + (((size_t)sb_ * Pl + (valid ? pair : 0)) * L + (valid ? site : 0)) * PF_D;
+      if (++spg_ == tm.nPG) { spg_ = 0; if (++sw_ == tm.nW) { sw_ = 0; ++sb_; } }
+      if (++s_slot3 == 3) { s_slot3 = 0; s_par3 ^= 1; }
+#pragma unroll
+      for (int jc = 0; jc < 4; jc += 2) {
+        uint32_t v0[16], v1[16];
+        tmem_ld16(tmem + s_lane_base + WS_COL_D2 + 64 * a + 16 * jc, v0);
+        tmem_ld16(tmem + s_lane_base + WS_COL_D2 + 64 * a + 16 * jc + 16, v1);
+        tc_wait_ld();
+        if (dump != nullptr && blockIdx.x == 0 && s_first) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            dump[sr * 320 + 256 + 16 * jc + i] = __uint_as_float(v0[i]);
+            dump[sr * 320 + 256 + 16 * jc + 16 + i] = __uint_as_float(v1[i]);
+          }
+        }
+        if (valid) {
+          stg256(dst + 16 * jc, v0);
+          stg256(dst + 16 * jc + 8, v0 + 8);
+          stg256(dst + 16 * jc + 16, v1);
+          stg256(dst + 16 * jc + 24, v1 + 8);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(BAR(4 + a));
+      s_first = false;
+    };
+    if (warp != WS_MW) {
+#pragma unroll 1
+      for (int it = 0; it < n_my; ++it) store_tile();
+    }
+#endif
     if (warp == WS_MW) {
     // =============================== MMA ISSUER =============================================
     // The whole warp walks the loop (so descriptors live in uniform registers); one elected lane
@@ -607,6 +662,9 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
         }
         __syncwarp();
         TOC(3, t0);
+#if WS_STORE_WARPS
+        if (step >= 0 && half == 1) store_tile();   // tile `it`: its GEMM2 was just committed; nothing to issue meanwhile
+#endif
       }
     }
     }
@@ -709,11 +767,13 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
         e1(half, dump_this);
         mbar_arrive(BAR(9 + half));
       }
+#if !WS_STORE_WARPS
       if (half == 0 && step > 0) {   // after E1a(it): store tile it-1 (also the final tile at step == 2 n_my)
         const long long t0 = TIC();
         e2();
         TOC(5, t0);
       }
+#endif
     }
   }
   if (PROF && dump != nullptr && (tid == WS_PW0 * 32 || tid == WS_MW * 32 || tid == WS_EW0 * 32)) {
