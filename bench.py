@@ -47,6 +47,11 @@ WORKLOADS = {                         # name -> (B, n, L)
 }
 
 
+def workload_desc(name):
+    B, n, L = WORKLOADS[name]
+    return f"PF {name}: B={B} MSAs of {n} taxa x {L} sites, {n * (n - 1) // 2} pairs each, pf.ckpt weights"
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -183,7 +188,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"PF {args.workload} (pf.ckpt weights); CPU arm runs a bounded sample: {sample}"},
+        "config": {"workload": workload_desc(args.workload), "tokens_per_step": tokens, "precision": "fp32",
+                   "parallelism": f"host CPU, {threads} threads (rank 0 only)",
+                   "sample": f"each step is a bounded sample of the workload: {sample}"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -337,7 +344,7 @@ def run_native(args):
         "scaling": "weak" if batch_sharded else "strong", "vs_baseline": None,
         "dtype": {"fp32": "f32", "bf16x3": "f32 (FFN: bf16x3 tcgen05, f32 accumulate)", "bf16": "f32 (FFN: bf16 tcgen05)"}[args.precision],
         "data": "synthetic",
-        "config": {"workload": f"PF {args.workload}: B={B} MSAs of {n} taxa x {L} sites, {P} pairs each, pf.ckpt weights",
+        "config": {"workload": workload_desc(args.workload),
                    "tokens_per_step": tokens, "precision": args.precision,
                    "parallelism": ("1 GPU" if world == 1 else (f"batch-sharded x{world} (replicas)" if batch_sharded
                                                                else f"pair-sharded x{world}, all-reduce of (L,72) fp32 per block")),
