@@ -569,7 +569,7 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
         tmem_ld16(tmem + s_lane_base + WS_COL_D2 + 64 * a + 16 * jc, v0);
         tmem_ld16(tmem + s_lane_base + WS_COL_D2 + 64 * a + 16 * jc + 16, v1);
         tc_wait_ld();
-        if (dump != nullptr && blockIdx.x == 0 && s_first) {
+        if (PROF && dump != nullptr && blockIdx.x == 0 && s_first) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             dump[sr * 320 + 256 + 16 * jc + i] = __uint_as_float(v0[i]);
@@ -679,7 +679,7 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
       uint32_t v[2][16];
       auto col_of = [&](int i) { return half * 128 + (chf + i * WS_NCG) * 16; };   // TMEM column == hidden unit
       auto chunk = [&](const uint32_t(&vc)[16], int cc) {
-        if (dump_this) {
+        if (PROF && dump_this) {   // debug builds only: predicated-off stores still cost issue slots
 #pragma unroll
           for (int i = 0; i < 16; ++i) dump[r * 320 + cc + i] = __uint_as_float(vc[i]);
         }
@@ -739,7 +739,7 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
           uint32_t v[16];
           tmem_ld16(tmem + lane_base + WS_COL_D2 + 64 * a + 16 * jc, v);
           tc_wait_ld();
-          if (dump != nullptr && blockIdx.x == 0 && first_e2) {
+          if (PROF && dump != nullptr && blockIdx.x == 0 && first_e2) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) dump[r * 320 + 256 + 16 * jc + i] = __uint_as_float(v[i]);
           }
@@ -802,7 +802,7 @@ inline int pf_ffn_ws_launch(const PfFfnConst& kc, const PfFfnTcW* Wt, float* x, 
   const long long nt = (long long)B * ((L + WS_S - 1) / WS_S) * ((Pl + WS_G - 1) / WS_G);
   if (nt > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
   const int grid = (int)(nt < n_sm ? nt : n_sm);
-  if (prof)
+  if (prof || dump != nullptr)   // the debug/profiling instantiation carries the dump and the role timers
     k_colapply_ffn_ws<true><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(kc, Wt, x, colM, L, Pl, B, n_terms, err_flag, dump);
   else
     k_colapply_ffn_ws<false><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(kc, Wt, x, colM, L, Pl, B, n_terms, err_flag, dump);
