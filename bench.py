@@ -62,6 +62,8 @@ def parse_args():
     ap.add_argument("--precision", default=os.environ.get("PF_PRECISION", "bf16x3"),
                     choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "p2p"],
+                    help="cross-shard sum of the column summaries: library kernels over NVLink peer memory, or NCCL")
     return ap.parse_args()
 
 
@@ -225,7 +227,7 @@ def run_native(args):
     model = model.to(dev).eval()
     batch_sharded = world > 1 and B >= world
     if world > 1 and not batch_sharded:
-        model.shard_pairs()
+        model.shard_pairs(exchange=args.exchange)
     idx_host = pf_oracle.synth_msa(n, L, seed=1337 + n, kind="tree", B=B)
     if batch_sharded:  # independent MSAs: replicas, no collective
         from phyloformer_b200 import sharding
@@ -347,7 +349,8 @@ def run_native(args):
         "config": {"workload": workload_desc(args.workload),
                    "tokens_per_step": tokens, "precision": args.precision,
                    "parallelism": ("1 GPU" if world == 1 else (f"batch-sharded x{world} (replicas)" if batch_sharded
-                                                               else f"pair-sharded x{world}, all-reduce of (L,72) fp32 per block")),
+                                                               else f"pair-sharded x{world}, sum of (L,72) fp32 per block over "
+                                                                    + ("NVLink peer memory (own kernels)" if getattr(model, "_peer", None) else "NCCL all-reduce"))),
                    "l2": "activations (%.2f GB per rank) exceed L2; no flush needed" % (local_tokens * 256 / 1e9)},
         "clocks": clocks,
         "e2e": {"value": tokens / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,

@@ -114,6 +114,17 @@ int pf_dist_to_matrix(const float* dist_dev, int B, int n, float* mat_dev, void*
  * gpu_launches claim). */
 int pf_last_launch_count(pf_handle h);
 
+/* Pair-sharded column attention over NVLink peer memory instead of the reduce callback.
+ * Every rank allocates one symmetric buffer of pf_peer_exchange_bytes(slot_floats) bytes, zero
+ * filled, and maps all ranks' buffers (CUDA IPC / torch symmetric memory); peer_bufs_host[r] is
+ * rank r's buffer as addressable from THIS process.  slot_floats >= B*L*72 of the largest
+ * forward.  After this call pf_forward ignores `reduce` for partial pair ranges: the library's
+ * own kernels publish, synchronise (system-scope flags) and read the (B,L,72) summaries with
+ * plain P2P loads, summing in rank order.  world <= 1 or NULL disables it again.
+ * Every rank must issue the same sequence of forwards. */
+int pf_set_peer_exchange(pf_handle h, int rank, int world, void* const* peer_bufs_host, size_t slot_floats);
+size_t pf_peer_exchange_bytes(size_t slot_floats);
+
 /* Synchronises and returns PF_ERR_CUDA if a kernel raised the device-side error flag (a
  * tensor-core pipeline wait that timed out instead of hanging the GPU); clears the flag. */
 int pf_device_error(pf_handle h);

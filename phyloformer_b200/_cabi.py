@@ -39,6 +39,8 @@ SYMBOLS = {
                                  c_void_p, c_void_p, c_size_t, c_void_p, REDUCE_FN, c_void_p, c_int, c_void_p]),
     "pf_dist_to_matrix": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "pf_last_launch_count": (c_int, [c_void_p]),
+    "pf_set_peer_exchange": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p), c_size_t]),
+    "pf_peer_exchange_bytes": (c_size_t, [c_size_t]),
     "pf_device_error": (c_int, [c_void_p]),
     "pf_debug_set_dump": (c_int, [c_void_p, c_void_p]),
     "pf_profile_enable": (c_int, [c_void_p, c_int]),

@@ -57,6 +57,12 @@ struct pf_ctx {
   int launches = 0;
   int ffn_impl = 1;             // 0: pf_ffn_tc.cuh (phased), 1: pf_ffn_ws.cuh (warp-specialised); env PF_FFN_IMPL=tc|ws
   int row_impl = 1;             // 0: k_row_attn<0> (register loads), 1: k_row_attn_tma (bulk-copy ring); env PF_ROW_IMPL=ld|tma
+  // peer-memory exchange (pf_set_peer_exchange): symmetric buffers of all ranks, mapped locally
+  int peer_rank = 0, peer_world = 0;
+  unsigned char** peers_dev = nullptr;   // [world] device array of buffer base pointers
+  unsigned char* peer_self = nullptr;    // this rank's buffer
+  size_t peer_slot_floats = 0;
+  unsigned peer_epoch = 0;
   int ws_prof = 0;              // env PF_WS_PROF=1: role timing into the dump buffer (test hook)
   int* err_dev = nullptr;       // set by a kernel whose mbarrier wait timed out
   float* dump_dev = nullptr;    // test hook: raw accumulators of the first FFN tile
@@ -286,6 +292,7 @@ void pf_destroy(pf_handle h) {
   if (h->blk_dev) cudaFree(h->blk_dev);
   if (h->tc_dev) cudaFree(h->tc_dev);
   if (h->err_dev) cudaFree(h->err_dev);
+  if (h->peers_dev) cudaFree(h->peers_dev);
   for (auto& r : h->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : h->pool) cudaEventDestroy(e);
   delete h;
@@ -326,8 +333,8 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
   const long long P = (long long)n * (n - 1) / 2;
   if (pair_lo < 0 || pair_hi > P || pair_hi <= pair_lo)
     return fail(PF_ERR_ARG, "pf_forward: bad pair range [%lld,%lld) of %lld", (long long)pair_lo, (long long)pair_hi, P);
-  if ((pair_hi - pair_lo) != P && reduce == nullptr)
-    return fail(PF_ERR_ARG, "pf_forward: a partial pair range needs a reduce callback");
+  if ((pair_hi - pair_lo) != P && reduce == nullptr && h->peer_world <= 1)
+    return fail(PF_ERR_ARG, "pf_forward: a partial pair range needs a reduce callback or a peer exchange");
   if (!dist_dev && n_stages < 0) return fail(PF_ERR_ARG, "pf_forward: null dist buffer");
   const Plan pl = make_plan(h, B, n, L, pair_lo, pair_hi);
   if (ws_bytes < pl.total) return fail(PF_ERR_WORKSPACE, "pf_forward: workspace %zu < %zu bytes", ws_bytes, pl.total);
@@ -395,20 +402,44 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
         k_col_partial<<<g, 256, 0, st>>>(&bw->col, x, part, L, (int)pl.Pl, pl.ppc);
       }
       dim3 g2(L, B);
-      {
-        Timed t_(h, PF_KC_COLFIN, st);
-        k_col_reduce<<<g2, 64, 0, st>>>(&bw->col, part, pl.n_chunks, L, colsum);
+      const bool peer = (h->peer_world > 1) && ((pair_hi - pair_lo) != P);
+      if (peer) {
+        const size_t need = (size_t)B * L * PF_COLSUM;
+        if (need > h->peer_slot_floats)
+          return fail(PF_ERR_ARG, "pf_forward: peer exchange slot holds %zu floats, need %zu", h->peer_slot_floats, need);
+        const unsigned epoch = ++h->peer_epoch;
+        const int slot = (int)(epoch & 1u);
+        float* my_slot = reinterpret_cast<float*>(h->peer_self + PF_PEER_FLAG_BYTES) + (size_t)slot * h->peer_slot_floats;
+        {
+          Timed t_(h, PF_KC_COLFIN, st);
+          k_col_reduce<<<g2, 64, 0, st>>>(&bw->col, part, pl.n_chunks, L, my_slot);
+        }
+        {
+          Timed t_(h, PF_KC_COLFIN, st);
+          k_peer_sync<<<1, 32, 0, st>>>(h->peers_dev, h->peer_rank, h->peer_world, epoch, h->err_dev);
+        }
+        {
+          Timed t_(h, PF_KC_COLFIN, st);
+          k_col_finalize_peer<<<g2, 256, 0, st>>>(&bw->col, h->peers_dev, h->peer_world, slot, h->peer_slot_floats,
+                                                  (float)P, L, colM);
+        }
+        CUDA_TRY(cudaGetLastError());
+      } else {
+        {
+          Timed t_(h, PF_KC_COLFIN, st);
+          k_col_reduce<<<g2, 64, 0, st>>>(&bw->col, part, pl.n_chunks, L, colsum);
+        }
+        CUDA_TRY(cudaGetLastError());
+        if (reduce) {
+          const int rc = reduce(reduce_user, colsum, (size_t)B * L * PF_COLSUM, stream);
+          if (rc != 0) return fail(PF_ERR_REDUCE, "pf_forward: reduce callback returned %d", rc);
+        }
+        {
+          Timed t_(h, PF_KC_COLFIN, st);
+          k_col_finalize<<<g2, 256, 0, st>>>(&bw->col, colsum, (float)P, L, colM);
+        }
+        CUDA_TRY(cudaGetLastError());
       }
-      CUDA_TRY(cudaGetLastError());
-      if (reduce) {
-        const int rc = reduce(reduce_user, colsum, (size_t)B * L * PF_COLSUM, stream);
-        if (rc != 0) return fail(PF_ERR_REDUCE, "pf_forward: reduce callback returned %d", rc);
-      }
-      {
-        Timed t_(h, PF_KC_COLFIN, st);
-        k_col_finalize<<<g2, 256, 0, st>>>(&bw->col, colsum, (float)P, L, colM);
-      }
-      CUDA_TRY(cudaGetLastError());
     }
     // ---- column apply + FFN ----
     const bool apply_only = dbg && (n_stages == 3 * b + 2);
@@ -459,6 +490,24 @@ int pf_dist_to_matrix(const float* dist_dev, int B, int n, float* mat_dev, void*
 }
 
 int pf_last_launch_count(pf_handle h) { return h ? h->launches : 0; }
+
+int pf_set_peer_exchange(pf_handle h, int rank, int world, void* const* peer_bufs_host, size_t slot_floats) {
+  if (!h) return fail(PF_ERR_ARG, "pf_set_peer_exchange: null handle");
+  if (h->peers_dev) { cudaFree(h->peers_dev); h->peers_dev = nullptr; }
+  h->peer_world = 0;
+  if (world <= 1 || peer_bufs_host == nullptr) return PF_OK;   // exchange disabled
+  if (rank < 0 || rank >= world || world > 32) return fail(PF_ERR_ARG, "pf_set_peer_exchange: bad rank/world %d/%d", rank, world);
+  CUDA_TRY(cudaMalloc(&h->peers_dev, sizeof(void*) * world));
+  CUDA_TRY(cudaMemcpy(h->peers_dev, peer_bufs_host, sizeof(void*) * world, cudaMemcpyHostToDevice));
+  h->peer_self = (unsigned char*)peer_bufs_host[rank];
+  h->peer_rank = rank;
+  h->peer_world = world;
+  h->peer_slot_floats = slot_floats;
+  h->peer_epoch = 0;
+  return PF_OK;
+}
+
+size_t pf_peer_exchange_bytes(size_t slot_floats) { return PF_PEER_FLAG_BYTES + 2 * slot_floats * sizeof(float); }
 
 int pf_device_error(pf_handle h) {
   if (!h) return fail(PF_ERR_ARG, "pf_device_error: null handle");

@@ -793,6 +793,63 @@ k_colapply_ffn_fp32(const PfAttnW* __restrict__ Wc, const PfFfnW* __restrict__ W
 // Distance head: dist[b,p] = mean_l softplus(w . x[b,p,l,:] + c)        model.py:158-164,182-185
 // One CTA per pair-row; fixed-order reduction over the sites.
 // ------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------
+// Pair-sharded column attention over NVLink peer memory (no NCCL on the data path).
+// Every rank owns a symmetric exchange buffer, mapped into all peers:
+//     [ flags: 64 x uint32 ][ slot 0: B*L*72 floats ][ slot 1: B*L*72 floats ]
+// k_col_reduce writes this rank's 72-float summaries into slot (epoch & 1) of its own buffer;
+// k_peer_sync publishes "epoch reached" into every peer's flag word [rank] (system-scope
+// release after a system fence) and waits until all peers have published the same epoch
+// (acquire); k_col_finalize_peer then reads the same slot of every rank with plain P2P loads
+// and sums in rank order (identical on every rank, deterministic).  Two slots suffice: a slot is
+// rewritten two exchanges later, and a rank only gets past the next exchange's sync after every
+// peer has finished reading the previous one.
+// ------------------------------------------------------------------------------------------
+#define PF_PEER_FLAG_BYTES 256
+
+__global__ void k_peer_sync(unsigned char* const* __restrict__ peers, int rank, int world, unsigned epoch,
+                            int* __restrict__ err_flag) {
+  const int t = threadIdx.x;
+  if (t >= world) return;
+  __threadfence_system();  // this rank's summaries (written by the previous kernel) before the flag
+  volatile unsigned* remote = reinterpret_cast<volatile unsigned*>(peers[t]) + rank;
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+  const unsigned* mine = reinterpret_cast<const unsigned*>(peers[rank]) + t;
+  unsigned v = 0;
+  for (unsigned spin = 0; spin < (1u << 26); ++spin) {   // bounded (~seconds): never hang the GPU
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    if ((int)(v - epoch) >= 0) return;
+    __nanosleep(64);
+  }
+  if (err_flag != nullptr) *err_flag = 3;
+}
+
+__global__ void __launch_bounds__(256)
+k_col_finalize_peer(const PfAttnW* __restrict__ W, unsigned char* const* __restrict__ peers, int world, int slot,
+                    size_t slot_floats, float p_total, int L, float* __restrict__ colM) {
+  __shared__ float tot[PF_COLSUM];
+  __shared__ float ctx[PF_D];
+  const int t = threadIdx.x, l = blockIdx.x, b = blockIdx.y;
+  if (t < PF_COLSUM) {
+    float s = 0.f;
+    for (int r = 0; r < world; ++r) {  // fixed rank order
+      const float* src = reinterpret_cast<const float*>(peers[r] + PF_PEER_FLAG_BYTES) + (size_t)slot * slot_floats;
+      s += src[((size_t)b * L + l) * PF_COLSUM + t];
+    }
+    tot[t] = s;
+  }
+  __syncthreads();
+  float* o = colM + ((size_t)b * L + l) * PF_MROW;
+  if (t < PF_D) ctx[t] = tot[8 + t] / tot[t >> 4];
+  if (t < PF_H) o[256 + t] = p_total / tot[4 + t];
+  __syncthreads();
+  const int c = t >> 2, h = t & 3;
+  float acc = 0.f;
+#pragma unroll
+  for (int e = 0; e < PF_DH; ++e) acc = fmaf(W->wo[c][h * PF_DH + e], ctx[h * PF_DH + e], acc);
+  o[c * 4 + h] = acc;
+}
+
 __global__ void __launch_bounds__(256)
 k_head(const PfHeadW* __restrict__ hw, const float* __restrict__ x, int L, float* __restrict__ dist) {
   __shared__ float red[32];

@@ -101,6 +101,9 @@ class Phyloformer(nn.Module):
         self._handle_key = None
         self._ws = None
         self._shard = None  # (group, rank, world)
+        self._exchange = "auto"
+        self._peer = None
+        self._peer_failed = False
         self._reduce_cb = None
         self.last_launches = 0
 
@@ -153,15 +156,57 @@ class Phyloformer(nn.Module):
             _cabi.check(_cabi.load().pf_set_precision(self._handle, _cabi.PRECISIONS[precision]), "pf_set_precision")
 
     # ------------------------------------------------------------------ sharding
-    def shard_pairs(self, group=None):
+    def shard_pairs(self, group=None, exchange: str = "auto"):
         """Shard the pair axis over `group` (default: the world group). Every rank must call
-        forward with the same input; every rank gets the full result."""
+        forward with the same input; every rank gets the full result.
+
+        exchange: how the per-block (B,L,72) column summaries are summed across ranks
+          "nccl"  torch.distributed.all_reduce through the C ABI's reduce callback
+          "p2p"   the library's own kernels over NVLink peer memory (torch symmetric memory
+                  provides the mapped buffers; no collective library on the data path)
+          "auto"  p2p when the backend is NCCL and symmetric memory can be set up, else nccl"""
         import torch.distributed as dist
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
+        if exchange not in ("auto", "nccl", "p2p"):
+            raise ValueError("exchange must be 'auto', 'nccl' or 'p2p'")
         world = dist.get_world_size(group)
         self._shard = (group, dist.get_rank(group), world) if world > 1 else None
+        self._exchange = exchange
+        self._peer = None          # (symmetric tensor, handle, slot_floats)
+        self._peer_failed = False
         return self
+
+    def _setup_peer_exchange(self, lib, need_floats, device):
+        """(Re)allocate the symmetric exchange buffer; collective over the shard group."""
+        import torch.distributed as dist
+        group, rank, world = self._shard
+        if self._exchange == "nccl" or self._peer_failed:
+            return False
+        if self._exchange == "auto" and dist.get_backend(group) != "nccl":
+            return False
+        if self._peer is not None and self._peer[2] >= need_floats:
+            return True
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            slot = int(need_floats)
+            nbytes = lib.pf_peer_exchange_bytes(slot)
+            buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+            buf.zero_()
+            torch.cuda.synchronize(device)
+            hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+            dist.barrier(group)           # every rank has zeroed its flags before anyone publishes
+            ptrs = (ctypes.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
+            _cabi.check(lib.pf_set_peer_exchange(self._handle, rank, world, ptrs, slot), "pf_set_peer_exchange")
+            self._peer = (buf, hdl, slot)
+            return True
+        except Exception as e:  # noqa: BLE001
+            if self._exchange == "p2p":
+                raise
+            import warnings
+            warnings.warn(f"peer-memory exchange unavailable ({e!r}); using NCCL all-reduce")
+            self._peer_failed = True
+            return False
 
     def _make_reduce(self, ws):
         import torch.distributed as dist
@@ -212,7 +257,9 @@ class Phyloformer(nn.Module):
                 ws = self._workspace(max(nbytes, 256), device)
                 cb = _cabi.NULL_REDUCE
                 if self._shard is not None:
-                    cb = self._make_reduce(ws)
+                    if not self._setup_peer_exchange(lib, B * L * _cabi.PF_COLSUM_FLOATS, device):
+                        _cabi.check(lib.pf_set_peer_exchange(self._handle, 0, 0, None, 0), "pf_set_peer_exchange")
+                    cb = self._make_reduce(ws)   # used only when the peer exchange is off
                     self._reduce_cb = cb  # keep alive for the duration of the call
                 xp = x.data_ptr() if x is not None else None
                 fp = flag.data_ptr() if flag is not None else None

@@ -31,9 +31,16 @@ def _worker(rank, world, port, backend, q):
         m = m.to(f"cuda:{dev}").eval()
         idx = pf_oracle.synth_msa(23, 150, seed=12, B=2).to(f"cuda:{dev}")
         full = m.forward_idx(idx, squeeze=False)          # unsharded on this rank
-        m.shard_pairs()
+        m.shard_pairs(exchange="nccl")
         sharded = m.forward_idx(idx, squeeze=False)       # pair range of this rank + exchange + gather
         m.check_device_error()
+        if backend == "nccl":                             # NVLink peer-memory exchange (library kernels)
+            m.shard_pairs(exchange="p2p")
+            p2p = m.forward_idx(idx, squeeze=False)
+            p2p_again = m.forward_idx(idx, squeeze=False)
+            m.check_device_error()
+            assert torch.equal(p2p, p2p_again)
+            assert torch.equal(p2p, sharded), float((p2p - sharded).abs().max())   # same rank-order sum
         q.put((rank, full.cpu().numpy(), sharded.cpu().numpy()))
     except Exception as e:  # noqa: BLE001
         import traceback
