@@ -6,3 +6,6 @@ mkdir -p baseline/_ref/bin
 cp /root/reference/bin/bin_linux/fastme baseline/_ref/bin/fastme
 chmod +x baseline/_ref/bin/fastme
 echo staged baseline/_ref/bin/fastme
+# the reference's own CLI, unmodified, for the drop-in test (tests/test_gpu_dropin.py)
+cp /root/reference/infer_alns.py baseline/_ref/infer_alns.py
+echo staged baseline/_ref/infer_alns.py
