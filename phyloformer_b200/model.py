@@ -329,6 +329,36 @@ class Phyloformer(nn.Module):
         out = self._run(msa, None, None, B, n, L)
         return torch.squeeze(out) if squeeze else out
 
+    def make_graphed(self, example_idx: torch.Tensor):
+        """Capture forward_idx for one input shape into a CUDA graph (the ~32 kernel launches of a
+        forward become one graph launch: small alignments are launch-bound otherwise).
+
+        Returns `run(idx) -> (B, P) distances`; `idx` must have the shape/dtype of `example_idx`.
+        The result tensor is reused between calls (clone it to keep it).  Not available while the
+        pair axis is sharded (the exchange is a host-driven collective)."""
+        if self._shard is not None:
+            raise RuntimeError("make_graphed is not supported with shard_pairs()")
+        ex = example_idx[None] if example_idx.dim() == 2 else example_idx
+        if ex.dtype != torch.uint8 or not ex.is_cuda:
+            raise TypeError("make_graphed expects a CUDA uint8 tensor of residue codes")
+        static_in = ex.contiguous().clone()
+        self.forward_idx(static_in, squeeze=False)          # warm-up: handle, workspace, lazy init
+        torch.cuda.synchronize(static_in.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_out = self.forward_idx(static_in, squeeze=False)
+
+        def run(idx: torch.Tensor) -> torch.Tensor:
+            idx = idx[None] if idx.dim() == 2 else idx
+            if idx.shape != static_in.shape or idx.dtype != torch.uint8:
+                raise ValueError(f"graphed forward expects uint8 {tuple(static_in.shape)}, got {idx.dtype} {tuple(idx.shape)}")
+            static_in.copy_(idx, non_blocking=True)
+            graph.replay()
+            return static_out
+
+        run.graph = graph  # keep alive / introspection
+        return run
+
     def debug_activation(self, input_or_idx, n_stages: int):
         """Test hook: activation (B,Pl,L,64) after `n_stages` sub-blocks (0 = pair embedding)."""
         t = input_or_idx
