@@ -111,7 +111,8 @@ Plan make_plan(const pf_ctx* h, int B, int n, int L, long long lo, long long hi)
     const long long ppc = (p.Pl + nc - 1) / nc;
     const long long chunks = (p.Pl + ppc - 1) / ppc;
     const long long waves = (per_chunk * chunks + slots - 1) / slots;
-    const long long cost = waves * ppc * 64 + chunks;  // small penalty on the number of partial buffers
+    // per-CTA start-up (weights into registers) ~ 16 pairs' worth; small penalty per partial buffer
+    const long long cost = waves * (ppc + 16) * 64 + chunks;
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_nc = nc; }
   }
   p.ppc = (int)((p.Pl + best_nc - 1) / best_nc);

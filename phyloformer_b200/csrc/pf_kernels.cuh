@@ -318,7 +318,8 @@ k_row_attn_tma(const PfAttnW* __restrict__ W, float* __restrict__ x, int L) {
   const uint32_t bar_u32 = (uint32_t)__cvta_generic_to_shared(bars);
 
   const int n_chunks = (L + RT_TOK - 1) / RT_TOK;
-  const int n_total = 2 * n_chunks;  // pass A then pass B over the same row
+  const bool resident = n_chunks <= RT_STAGES;             // short rows: the whole row stays in the ring
+  const int n_total = resident ? n_chunks : 2 * n_chunks;  // otherwise pass B streams the row again (L2 hit)
   auto issue = [&](int c) {          // thread 0 only
     const int cr = c < n_chunks ? c : c - n_chunks;
     const int tok0 = cr * RT_TOK;
@@ -454,9 +455,9 @@ k_row_attn_tma(const PfAttnW* __restrict__ W, float* __restrict__ x, int L) {
     bo[i] = W->bo[c];
   }
   const float4 qi = *reinterpret_cast<const float4*>(sm.qinv);
-  for (int c = n_chunks; c < n_total; ++c) {
-    const int st = c % RT_STAGES;
-    rt_wait(bar_u32 + 8 * st, (uint32_t)((c / RT_STAGES) & 1));
+  for (int c = n_chunks; c < 2 * n_chunks; ++c) {
+    const int st = resident ? (c - n_chunks) : (c % RT_STAGES);
+    if (!resident) rt_wait(bar_u32 + 8 * st, (uint32_t)((c / RT_STAGES) & 1));
     const float* stage = reinterpret_cast<const float*>(ring + st * RT_STAGE_BYTES);
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -479,10 +480,12 @@ k_row_attn_tma(const PfAttnW* __restrict__ W, float* __restrict__ x, int L) {
         store_tok(xrow + (size_t)l * PF_D, j, xc);
       }
     }
-    __syncthreads();
-    if (tid == 0 && c + RT_STAGES < n_total) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      issue(c + RT_STAGES);
+    if (!resident) {
+      __syncthreads();
+      if (tid == 0 && c + RT_STAGES < n_total) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(c + RT_STAGES);
+      }
     }
   }
 }
