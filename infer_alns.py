@@ -12,8 +12,9 @@ the GPU as (n, L) uint8 residue codes instead of a 22-channel fp32 one-hot, alig
 same shape are run as one batched forward (the reference loops file by file,
 infer_alns.py:97-112), the symmetric matrix is assembled on the device, the text is formatted
 in one vectorised pass, and -t falls back to a built-in neighbour joining when scikit-bio is
-not installed.  Extra environment knobs: PF_PRECISION=fp32|bf16x3|bf16,
-PF_MAX_BATCH_TOKENS (pair*sites per batched call, default 2e7).
+not installed; parsing, device work and file output overlap (run_pipeline).  Extra environment
+knobs: PF_PRECISION=fp32|bf16x3|bf16, PF_MAX_BATCH_TOKENS (pair*sites per batched call,
+default 2e7).
 """
 import argparse
 import os
@@ -96,34 +97,86 @@ def main(argv=None):
     out_dir = os.path.abspath(args.outdir)
     os.makedirs(out_dir, exist_ok=True)
 
-    # parse everything first (host), bucket by alignment shape
     paths = sorted(glob(f"{in_dir}/*"))
     for alnpath in paths:
         if not has_fasta_ext(alnpath):
             raise ValueError("Input files must be fasta files (.fa or .fasta). Got " f"{alnpath}")
-    buckets = {}
-    for alnpath in paths:
-        idx, ids = load_alignment_idx(alnpath)
-        buckets.setdefault(tuple(idx.shape), []).append((alnpath, idx, ids))
     max_tokens = float(os.environ.get("PF_MAX_BATCH_TOKENS", 2e7))
-
     with torch.no_grad(), tqdm(total=len(paths)) as bar:
-        for (n, L), items in buckets.items():
+        run_pipeline(model, paths, out_dir, nj, max_tokens, bar.update)
+
+
+def write_outputs(out_dir, chunk, mats, nj):
+    """Host-side tail for one batched call: PHYLIP text (and optionally the NJ tree) per file."""
+    for (alnpath, _, ids), dm in zip(chunk, mats):
+        stem = Path(alnpath).stem
+        with open(os.path.join(out_dir, f"{stem}.phy"), "w") as outfile:
+            outfile.write(matrix_to_phylip(dm, ids))
+        if nj is not None:
+            with open(os.path.join(out_dir, f"{stem}.nj.nwk"), "w") as outfile:
+                outfile.write(nj(dm.astype(np.float64), ids))
+    return len(chunk)
+
+
+def run_pipeline(model, paths, out_dir, nj, max_tokens, progress=lambda k: None, depth=2):
+    """Three overlapped stages (the reference does them serially per file, infer_alns.py:97-117):
+
+      parse pool   FASTA -> (n, L) uint8 codes, several files at a time
+      device       alignments of one shape are stacked into a pinned staging buffer, copied
+                   H2D, run as ONE batched forward, symmetrised on the device and copied D2H into
+                   a pinned result buffer, all asynchronously on the current stream; up to `depth`
+                   batches are in flight before the host waits for the oldest one
+      write pool   '%.10f' formatting + file output of finished batches
+    """
+    from collections import deque
+    from concurrent.futures import ThreadPoolExecutor
+
+    device = next(model.parameters()).device
+    n_cpu = os.cpu_count() or 1
+    inflight = deque()
+    writes = []
+
+    def launch(chunk, n, L):
+        stage = torch.empty((len(chunk), n, L), dtype=torch.uint8).pin_memory()
+        for k, it in enumerate(chunk):
+            stage[k].copy_(it[1])
+        batch = stage.to(device, non_blocking=True)                      # (B,n,L) uint8
+        preds = model.forward_idx(batch, squeeze=False)                  # (B,P)
+        mats_dev = model.distance_matrix(preds, n)                       # (B,n,n)
+        mats = torch.empty(mats_dev.shape, dtype=mats_dev.dtype).pin_memory()
+        mats.copy_(mats_dev, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        inflight.append((chunk, stage, mats, done))
+
+    def retire(pool):
+        chunk, _stage, mats, done = inflight.popleft()
+        done.synchronize()
+        writes.append(pool.submit(write_outputs, out_dir, chunk, mats.numpy(), nj))
+
+    with ThreadPoolExecutor(max(1, min(8, n_cpu))) as parse_pool, \
+            ThreadPoolExecutor(max(1, min(4, n_cpu))) as write_pool:
+        buckets = {}
+        for alnpath, (idx, ids) in zip(paths, parse_pool.map(load_alignment_idx, paths)):
+            n, L = idx.shape
             per_msa = max(1, n * (n - 1) // 2 * L)
             step = max(1, int(max_tokens // per_msa))
-            for lo in range(0, len(items), step):
-                chunk = items[lo:lo + step]
-                batch = torch.stack([it[1] for it in chunk]).to(device, non_blocking=True)   # (B,n,L) uint8
-                preds = model.forward_idx(batch, squeeze=False)                              # (B,P)
-                mats = model.distance_matrix(preds, n).cpu().numpy()                         # (B,n,n)
-                for (alnpath, _, ids), dm in zip(chunk, mats):
-                    stem = Path(alnpath).stem
-                    with open(os.path.join(out_dir, f"{stem}.phy"), "w") as outfile:
-                        outfile.write(matrix_to_phylip(dm, ids))
-                    if nj is not None:
-                        with open(os.path.join(out_dir, f"{stem}.nj.nwk"), "w") as outfile:
-                            outfile.write(nj(dm.astype(np.float64), ids))
-                    bar.update(1)
+            items = buckets.setdefault((n, L), [])
+            items.append((alnpath, idx, ids))
+            if len(items) >= step:
+                launch(buckets.pop((n, L)), n, L)
+                while len(inflight) > depth:
+                    retire(write_pool)
+            while writes and writes[0].done():
+                progress(writes.pop(0).result())
+        for (n, L), items in buckets.items():        # partially filled buckets
+            launch(items, n, L)
+            while len(inflight) > depth:
+                retire(write_pool)
+        while inflight:
+            retire(write_pool)
+        for w in writes:
+            progress(w.result())
 
 
 if __name__ == "__main__":

@@ -402,7 +402,11 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
         Timed t_(h, PF_KC_COLSUM, st);
         k_col_partial<<<g, 256, 0, st>>>(&bw->col, x, part, L, (int)pl.Pl, pl.ppc);
       }
-      dim3 g2(L, B);
+      // column reduce/finalize: spc sites per CTA (weights stay in registers across them), about
+      // two CTAs per SM when there are few sites, PF_FS per CTA for batches of small alignments
+      const int n_sites = B * L;
+      const int spc = std::max(1, std::min(PF_FS, n_sites / (2 * h->n_sm)));
+      const unsigned gfs = (unsigned)((n_sites + spc - 1) / spc);
       const bool peer = (h->peer_world > 1) && ((pair_hi - pair_lo) != P);
       if (peer) {
         const size_t need = (size_t)B * L * PF_COLSUM;
@@ -413,7 +417,7 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
         float* my_slot = reinterpret_cast<float*>(h->peer_self + PF_PEER_FLAG_BYTES) + (size_t)slot * h->peer_slot_floats;
         {
           Timed t_(h, PF_KC_COLFIN, st);
-          k_col_reduce<<<g2, 64, 0, st>>>(&bw->col, part, pl.n_chunks, L, my_slot);
+          k_col_reduce<<<gfs, 256, 0, st>>>(&bw->col, part, pl.n_chunks, n_sites, spc, my_slot);
         }
         {
           Timed t_(h, PF_KC_COLFIN, st);
@@ -421,14 +425,14 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
         }
         {
           Timed t_(h, PF_KC_COLFIN, st);
-          k_col_finalize_peer<<<g2, 256, 0, st>>>(&bw->col, h->peers_dev, h->peer_world, slot, h->peer_slot_floats,
-                                                  (float)P, L, colM);
+          k_col_finalize_peer<<<gfs, 256, 0, st>>>(&bw->col, h->peers_dev, h->peer_world, slot, h->peer_slot_floats,
+                                                   (float)P, n_sites, spc, colM);
         }
         CUDA_TRY(cudaGetLastError());
       } else {
         {
           Timed t_(h, PF_KC_COLFIN, st);
-          k_col_reduce<<<g2, 64, 0, st>>>(&bw->col, part, pl.n_chunks, L, colsum);
+          k_col_reduce<<<gfs, 256, 0, st>>>(&bw->col, part, pl.n_chunks, n_sites, spc, colsum);
         }
         CUDA_TRY(cudaGetLastError());
         if (reduce) {
@@ -437,7 +441,7 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
         }
         {
           Timed t_(h, PF_KC_COLFIN, st);
-          k_col_finalize<<<g2, 256, 0, st>>>(&bw->col, colsum, (float)P, L, colM);
+          k_col_finalize<<<gfs, 256, 0, st>>>(&bw->col, colsum, (float)P, n_sites, spc, colM);
         }
         CUDA_TRY(cudaGetLastError());
       }

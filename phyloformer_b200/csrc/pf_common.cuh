@@ -19,6 +19,7 @@
 #define PF_NCHAR 22
 #define PF_COLSUM 72   // exchange layout: sum k~ (4) | sum q~ (4) | sum k~ v (64)
 #define PF_PART 264    // local partial:   sum k~ (4) | sum q~ (4) | sum k~ n (4 x 64), n = LN without affine
+#define PF_FS 8        // sites per CTA in the column reduce / finalize kernels
 #define PF_MROW 260    // applied form:    M[64][4] | qinv[4]
 #define PF_FULL 0xffffffffu
 

@@ -64,11 +64,43 @@ struct RowSmem {
   float red[8][PF_PART];   // per-warp partial sums
   float tot[PF_PART];
   float ubar[PF_H][PF_D];
+  float ctxp[4][PF_D];     // ctx partial sums over 16-wide slices of the contraction
   float ctx[PF_D];
   float M[PF_D][PF_H];
   float qinv[PF_H];
   float table[PF_NCHAR][PF_D];
 };
+
+// Per-row finalize (all 256 threads): totals -> ubar = LN-affine(sum k u / sum k) -> ctx = W_v ubar + b_v
+// -> M[:,h] = W_o[:, h-slice] ctx_h, qinv = L / sum q.  The 64x64 contraction for ctx is split
+// over 4 thread groups (16 terms each) and summed in a fixed order: with one 64-term chain per
+// thread this section was ~40 % of a CTA's lifetime on short rows (L = 200).
+__device__ __forceinline__ void row_finalize(const PfAttnW* __restrict__ W, RowSmem& sm, int tid, int L) {
+  {
+    const int h = tid >> 6, c = tid & 63;
+    sm.ubar[h][c] = fmaf(W->gamma[c], sm.tot[8 + h * PF_D + c] / sm.tot[h], W->beta[c]);
+  }
+  if (tid < PF_H) sm.qinv[tid] = (float)L / sm.tot[4 + tid];
+  __syncthreads();
+  {
+    const int o = tid & 63, part = tid >> 6, h = o >> 4;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc = fmaf(W->wvT[16 * part + k][o], sm.ubar[h][16 * part + k], acc);
+    sm.ctxp[part][o] = acc;
+  }
+  __syncthreads();
+  if (tid < PF_D) sm.ctx[tid] = (((W->bv[tid] + sm.ctxp[0][tid]) + sm.ctxp[1][tid]) + sm.ctxp[2][tid]) + sm.ctxp[3][tid];
+  __syncthreads();
+  {
+    const int c = tid >> 2, h = tid & 3;
+    float acc = 0.f;
+#pragma unroll
+    for (int e = 0; e < PF_DH; ++e) acc = fmaf(W->wo[c][h * PF_DH + e], sm.ctx[h * PF_DH + e], acc);
+    sm.M[c][h] = acc;
+  }
+  __syncthreads();
+}
 
 template <int MODE>
 __device__ __forceinline__ void row_fetch(const float* __restrict__ xrow, const RowSmem& sm,
@@ -220,30 +252,7 @@ k_row_attn(const PfAttnW* __restrict__ W, const PfHeadW* __restrict__ hw, float*
     sm.tot[t] = s;
   }
   __syncthreads();
-  // ---------------- per-row finalize ----------------
-  if (tid < PF_D) {
-#pragma unroll
-    for (int h = 0; h < PF_H; ++h)
-      sm.ubar[h][tid] = fmaf(W->gamma[tid], sm.tot[8 + h * PF_D + tid] / sm.tot[h], W->beta[tid]);
-  }
-  __syncthreads();
-  if (tid < PF_D) {
-    const int h = tid >> 4;
-    float acc = W->bv[tid];
-#pragma unroll 8
-    for (int k = 0; k < PF_D; ++k) acc = fmaf(W->wvT[k][tid], sm.ubar[h][k], acc);
-    sm.ctx[tid] = acc;
-  }
-  if (tid < PF_H) sm.qinv[tid] = (float)L / sm.tot[4 + tid];
-  __syncthreads();
-  {
-    const int c = tid >> 2, h = tid & 3;
-    float acc = 0.f;
-#pragma unroll
-    for (int e = 0; e < PF_DH; ++e) acc = fmaf(W->wo[c][h * PF_DH + e], sm.ctx[h * PF_DH + e], acc);
-    sm.M[c][h] = acc;
-  }
-  __syncthreads();
+  row_finalize(W, sm, tid, L);
   // ---------------- phase B: y = x + M qhat + bo ----------------
   float4 Mr[8];
   float bo[8];
@@ -422,29 +431,7 @@ k_row_attn_tma(const PfAttnW* __restrict__ W, float* __restrict__ x, int L) {
     sm.tot[t] = s;
   }
   __syncthreads();
-  if (tid < PF_D) {
-#pragma unroll
-    for (int h = 0; h < PF_H; ++h)
-      sm.ubar[h][tid] = fmaf(W->gamma[tid], sm.tot[8 + h * PF_D + tid] / sm.tot[h], W->beta[tid]);
-  }
-  __syncthreads();
-  if (tid < PF_D) {
-    const int h = tid >> 4;
-    float acc = W->bv[tid];
-#pragma unroll 8
-    for (int k = 0; k < PF_D; ++k) acc = fmaf(W->wvT[k][tid], sm.ubar[h][k], acc);
-    sm.ctx[tid] = acc;
-  }
-  if (tid < PF_H) sm.qinv[tid] = (float)L / sm.tot[4 + tid];
-  __syncthreads();
-  {
-    const int c = tid >> 2, h = tid & 3;
-    float acc = 0.f;
-#pragma unroll
-    for (int e = 0; e < PF_DH; ++e) acc = fmaf(W->wo[c][h * PF_DH + e], sm.ctx[h * PF_DH + e], acc);
-    sm.M[c][h] = acc;
-  }
-  __syncthreads();
+  row_finalize(W, sm, tid, L);
   // ---------------- pass B: y = x + M qhat + bo ----------------
   float4 Mr[8];
   float bo[8];
@@ -572,52 +559,79 @@ k_col_partial(const PfAttnW* __restrict__ W, const float* __restrict__ x, float*
 
 // Column attention, step 2: fixed-order sum over the chunks, then the linear map to the
 // 72-float exchange form:  sum_p k~ v = Wv[h] (g * sum_p k~ n + b sum_p k~) + bv[h] sum_p k~.
-//   grid = (L, B), 64 threads
-__global__ void __launch_bounds__(64)
-k_col_reduce(const PfAttnW* __restrict__ W, const float* __restrict__ part, int n_chunks, int L,
+//   grid = ceil(B L / spc) CTAs of 256 threads, spc <= PF_FS sites per CTA (host: about two CTAs per SM): a thread keeps its column of
+//   W_v in registers and reuses it for its sites (one 16 KB weight read per CTA instead of per
+//   site; batches of small alignments have tens of thousands of sites).  Summation orders are
+//   fixed and independent of the site's position in the CTA.
+__global__ void __launch_bounds__(256)
+k_col_reduce(const PfAttnW* __restrict__ W, const float* __restrict__ part, int n_chunks, int n_sites, int spc,
              float* __restrict__ colsum) {
-  __shared__ float ub[PF_H][PF_D];
-  __shared__ float sums[8];
-  const int t = threadIdx.x, l = blockIdx.x, b = blockIdx.y, B = gridDim.y;
-  float s[PF_H] = {0.f, 0.f, 0.f, 0.f};
-  float s8 = 0.f;
-  for (int ch = 0; ch < n_chunks; ++ch) {
-    const float* p = part + (((size_t)ch * B + b) * L + l) * PF_PART;
-#pragma unroll
-    for (int h = 0; h < PF_H; ++h) s[h] += p[8 + h * PF_D + t];
-    if (t < 8) s8 += p[t];
+  __shared__ float tot[PF_FS][PF_PART];
+  __shared__ float ub[PF_FS][PF_H][PF_D];
+  const int t = threadIdx.x, s0 = blockIdx.x * spc;   // spc <= PF_FS sites per CTA
+  const int ns = min(spc, n_sites - s0);
+  for (int i = t; i < ns * PF_PART; i += 256) {
+    const int sl = i / PF_PART, e = i - sl * PF_PART;
+    float a = 0.f;
+    for (int ch = 0; ch < n_chunks; ++ch) a += part[((size_t)ch * n_sites + s0 + sl) * PF_PART + e];
+    tot[sl][e] = a;
   }
-  if (t < 8) sums[t] = s8;
   __syncthreads();
+  for (int i = t; i < ns * PF_H * PF_D; i += 256) {
+    const int sl = i >> 8, h = (i >> 6) & 3, c = i & 63;
+    ub[sl][h][c] = fmaf(W->gamma[c], tot[sl][8 + h * PF_D + c], W->beta[c] * tot[sl][h]);
+  }
+  for (int i = t; i < ns * 8; i += 256) colsum[(size_t)(s0 + (i >> 3)) * PF_COLSUM + (i & 7)] = tot[i >> 3][i & 7];
+  __syncthreads();
+  const int o = t & 63, h = o >> 4;
+  float wv[PF_D];
 #pragma unroll
-  for (int h = 0; h < PF_H; ++h) ub[h][t] = fmaf(W->gamma[t], s[h], W->beta[t] * sums[h]);
-  __syncthreads();
-  const int h = t >> 4;
-  float acc = W->bv[t] * sums[h];
-#pragma unroll 8
-  for (int k = 0; k < PF_D; ++k) acc = fmaf(W->wvT[k][t], ub[h][k], acc);
-  float* o = colsum + ((size_t)b * L + l) * PF_COLSUM;
-  o[8 + t] = acc;
-  if (t < 8) o[t] = sums[t];
+  for (int k = 0; k < PF_D; ++k) wv[k] = W->wvT[k][o];
+  const float bvo = W->bv[o];
+  for (int sl = t >> 6; sl < ns; sl += 4) {
+    float acc = bvo * tot[sl][h];
+#pragma unroll
+    for (int k = 0; k < PF_D; ++k) acc = fmaf(wv[k], ub[sl][h][k], acc);
+    colsum[(size_t)(s0 + sl) * PF_COLSUM + 8 + o] = acc;
+  }
 }
 
 // Column attention, step 3 (after the cross-shard sum): ctx = kv / sum k,  M_l = Wo[:,h] ctx_h,
-// qinv = P / sum q~.     grid = (L, B), 256 threads
-__global__ void __launch_bounds__(256)
-k_col_finalize(const PfAttnW* __restrict__ W, const float* __restrict__ colsum, float p_total,
-               int L, float* __restrict__ colM) {
-  __shared__ float ctx[PF_D];
-  const int t = threadIdx.x, l = blockIdx.x, b = blockIdx.y;
-  const float* s = colsum + ((size_t)b * L + l) * PF_COLSUM;
-  float* o = colM + ((size_t)b * L + l) * PF_MROW;
-  if (t < PF_D) ctx[t] = s[8 + t] / s[t >> 4];
-  if (t < PF_H) o[256 + t] = p_total / s[4 + t];
+// qinv = P / sum q~.     grid = ceil(B L / PF_FS), 256 threads; thread (c, h) keeps its 16 W_o
+// weights in registers for the CTA's PF_FS sites.
+__device__ __forceinline__ void col_finalize_sites(const PfAttnW* __restrict__ W, const float (*tot)[PF_COLSUM], int ns,
+                                                   int s0, float p_total, float* __restrict__ colM,
+                                                   float (*ctx)[PF_D]) {
+  const int t = threadIdx.x;
+  for (int i = t; i < ns * PF_D; i += 256) {
+    const int sl = i >> 6, e = i & 63;
+    ctx[sl][e] = tot[sl][8 + e] / tot[sl][e >> 4];
+  }
+  for (int i = t; i < ns * PF_H; i += 256)
+    colM[(size_t)(s0 + (i >> 2)) * PF_MROW + 256 + (i & 3)] = p_total / tot[i >> 2][4 + (i & 3)];
   __syncthreads();
   const int c = t >> 2, h = t & 3;
-  float acc = 0.f;
+  float wo[PF_DH];
 #pragma unroll
-  for (int e = 0; e < PF_DH; ++e) acc = fmaf(W->wo[c][h * PF_DH + e], ctx[h * PF_DH + e], acc);
-  o[c * 4 + h] = acc;
+  for (int e = 0; e < PF_DH; ++e) wo[e] = W->wo[c][h * PF_DH + e];
+  for (int sl = 0; sl < ns; ++sl) {
+    float acc = 0.f;
+#pragma unroll
+    for (int e = 0; e < PF_DH; ++e) acc = fmaf(wo[e], ctx[sl][h * PF_DH + e], acc);
+    colM[(size_t)(s0 + sl) * PF_MROW + c * 4 + h] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_col_finalize(const PfAttnW* __restrict__ W, const float* __restrict__ colsum, float p_total,
+               int n_sites, int spc, float* __restrict__ colM) {
+  __shared__ float tot[PF_FS][PF_COLSUM];
+  __shared__ float ctx[PF_FS][PF_D];
+  const int t = threadIdx.x, s0 = blockIdx.x * spc;
+  const int ns = min(spc, n_sites - s0);
+  for (int i = t; i < ns * PF_COLSUM; i += 256) (&tot[0][0])[i] = colsum[(size_t)s0 * PF_COLSUM + i];
+  __syncthreads();
+  col_finalize_sites(W, tot, ns, s0, p_total, colM, ctx);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -829,28 +843,21 @@ __global__ void k_peer_sync(unsigned char* const* __restrict__ peers, int rank, 
 
 __global__ void __launch_bounds__(256)
 k_col_finalize_peer(const PfAttnW* __restrict__ W, unsigned char* const* __restrict__ peers, int world, int slot,
-                    size_t slot_floats, float p_total, int L, float* __restrict__ colM) {
-  __shared__ float tot[PF_COLSUM];
-  __shared__ float ctx[PF_D];
-  const int t = threadIdx.x, l = blockIdx.x, b = blockIdx.y;
-  if (t < PF_COLSUM) {
-    float s = 0.f;
+                    size_t slot_floats, float p_total, int n_sites, int spc, float* __restrict__ colM) {
+  __shared__ float tot[PF_FS][PF_COLSUM];
+  __shared__ float ctx[PF_FS][PF_D];
+  const int t = threadIdx.x, s0 = blockIdx.x * spc;
+  const int ns = min(spc, n_sites - s0);
+  for (int i = t; i < ns * PF_COLSUM; i += 256) {
+    float a = 0.f;
     for (int r = 0; r < world; ++r) {  // fixed rank order
       const float* src = reinterpret_cast<const float*>(peers[r] + PF_PEER_FLAG_BYTES) + (size_t)slot * slot_floats;
-      s += src[((size_t)b * L + l) * PF_COLSUM + t];
+      a += src[(size_t)s0 * PF_COLSUM + i];
     }
-    tot[t] = s;
+    (&tot[0][0])[i] = a;
   }
   __syncthreads();
-  float* o = colM + ((size_t)b * L + l) * PF_MROW;
-  if (t < PF_D) ctx[t] = tot[8 + t] / tot[t >> 4];
-  if (t < PF_H) o[256 + t] = p_total / tot[4 + t];
-  __syncthreads();
-  const int c = t >> 2, h = t & 3;
-  float acc = 0.f;
-#pragma unroll
-  for (int e = 0; e < PF_DH; ++e) acc = fmaf(W->wo[c][h * PF_DH + e], ctx[h * PF_DH + e], acc);
-  o[c * 4 + h] = acc;
+  col_finalize_sites(W, tot, ns, s0, p_total, colM, ctx);
 }
 
 __global__ void __launch_bounds__(256)

@@ -34,7 +34,7 @@ def load_alignment_idx(filepath):
         codes = _LUT[raw]
         bad = np.nonzero(codes == 255)[0]
         if bad.size:
-            raise KeyError(int(raw[bad[0]]))
+            raise KeyError(chr(int(raw[bad[0]])))   # same key the reference's LOOKUP[char] raises
         rows.append(codes)
     if len({len(r) for r in rows}) > 1:
         raise ValueError(f"{filepath}: sequences have different lengths")
