@@ -60,7 +60,7 @@ def parse_args():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="200x1000", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default=os.environ.get("PF_PRECISION", "bf16x3"),
-                    choices=["fp32", "bf16x3", "bf16"])
+                    choices=["fp32", "bf16x3", "bf16", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "p2p"],
                     help="cross-shard sum of the column summaries: library kernels over NVLink peer memory, or NCCL")
@@ -319,13 +319,13 @@ def run_native(args):
                     "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
                     "note": "fp32 FFMA mode is CUDA-core bound; HBM figure given for reference"}
     else:
-        issued = 3.0 if args.precision == "bf16x3" else 1.0
+        issued = {"bf16x3": 3.0, "fp16": 2.0}.get(args.precision, 1.0)
         tf = local_tokens * FLOP_PER_TOKEN_FFN / (ffn_avg * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
         roofline = {"kernel": "k_colapply_ffn_ws" if os.environ.get("PF_FFN_IMPL", "ws") != "tc" else "k_colapply_ffn_tc", "bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s",
                     "frac": tf / peak, "traffic": None, "achieved_issued": tf * issued, "frac_issued": tf * issued / peak,
                     "hbm_gbs": local_tokens * BYTES_PER_TOKEN_FFN / (ffn_avg * 1e-3) / 1e9,
-                    "note": f"useful FLOPs = 65536/token; {int(issued)} bf16 MMA passes issued per product"}
+                    "note": f"useful FLOPs = 65536/token; {int(issued)} 16-bit MMA passes issued per product"}
     # DRAM traffic of the dominant kernel from the committed ncu capture (same workload, 1 GPU)
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
@@ -344,7 +344,8 @@ def run_native(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak" if batch_sharded else "strong", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "bf16x3": "f32 (FFN: bf16x3 tcgen05, f32 accumulate)", "bf16": "f32 (FFN: bf16 tcgen05)"}[args.precision],
+        "dtype": {"fp32": "f32", "bf16x3": "f32 (FFN: bf16x3 tcgen05, f32 accumulate)", "bf16": "f32 (FFN: bf16 tcgen05)",
+                  "fp16": "f32 (FFN: fp16 activations x fp16 hi+lo weights, tcgen05, f32 accumulate)"}[args.precision],
         "data": "synthetic",
         "config": {"workload": workload_desc(args.workload),
                    "tokens_per_step": tokens, "precision": args.precision,

@@ -34,6 +34,7 @@ extern "C" {
 #define PF_PREC_FP32   0 /* fp32 FFMA everywhere ("exact" mode, ~1e-6 of the reference)      */
 #define PF_PREC_BF16X3 1 /* tcgen05 bf16 MMAs, 3-term hi/lo split, fp32 accumulate in TMEM   */
 #define PF_PREC_BF16   2 /* single bf16 tcgen05 pass (fast mode, reported separately)        */
+#define PF_PREC_FP16   3 /* fp16 activations (one rounding) x fp16 hi+lo weights, 2 passes   */
 
 #define PF_OK              0
 #define PF_ERR_ARG        -1

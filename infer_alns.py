@@ -13,7 +13,7 @@ same shape are run as one batched forward (the reference loops file by file,
 infer_alns.py:97-112), the symmetric matrix is assembled on the device, the text is formatted
 in one vectorised pass, and -t falls back to a built-in neighbour joining when scikit-bio is
 not installed; parsing, device work and file output overlap (run_pipeline).  Extra environment
-knobs: PF_PRECISION=fp32|bf16x3|bf16, PF_MAX_BATCH_TOKENS (pair*sites per batched call,
+knobs: PF_PRECISION=fp32|bf16x3|fp16|bf16, PF_MAX_BATCH_TOKENS (pair*sites per batched call,
 default 2e7).
 """
 import argparse

@@ -11,8 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PF_LIB", os.path.join(HERE, "libpf_sm100.so"))  # PF_LIB: A/B-test another build
 
 PF_ABI_VERSION = 1
-PF_PREC_FP32, PF_PREC_BF16X3, PF_PREC_BF16 = 0, 1, 2
-PRECISIONS = {"fp32": PF_PREC_FP32, "bf16x3": PF_PREC_BF16X3, "bf16": PF_PREC_BF16}
+PF_PREC_FP32, PF_PREC_BF16X3, PF_PREC_BF16, PF_PREC_FP16 = 0, 1, 2, 3
+PRECISIONS = {"fp32": PF_PREC_FP32, "bf16x3": PF_PREC_BF16X3, "bf16": PF_PREC_BF16, "fp16": PF_PREC_FP16}
 PF_COLSUM_FLOATS = 72
 KERNEL_CLASSES = ["input", "row", "colsum", "colfin", "ffn", "head"]
 

@@ -53,6 +53,7 @@ struct pf_ctx {
   PfHeadW* head_dev = nullptr;
   PfBlockW* blk_dev = nullptr;  // [nb]
   PfFfnTcW* tc_dev = nullptr;   // [nb] bf16 hi/lo smem images for the tcgen05 FFN
+  PfFfnTcW* tc16_dev = nullptr; // [nb] the same in fp16 (PF_PREC_FP16)
   std::vector<PfFfnConst> ffn_const;  // [nb] host copies passed as __grid_constant__ kernel parameters
   int launches = 0;
   int ffn_impl = 1;             // 0: pf_ffn_tc.cuh (phased), 1: pf_ffn_ws.cuh (warp-specialised); env PF_FFN_IMPL=tc|ws
@@ -242,13 +243,14 @@ int pf_create(pf_handle* out, const pf_cfg* cfg, const float* const* weights_dev
     head[0].bhead = hw.t[hb + 1][0];
   }
   std::vector<PfBlockW> blk(nb);
-  std::vector<PfFfnTcW> tc(nb);
+  std::vector<PfFfnTcW> tc(nb), tc16(nb);
   for (int b = 0; b < nb; ++b) {
     const int base = 2 + 26 * b;
     pack_attn(hw, base + 0, base + 16, &blk[b].row);
     pack_attn(hw, base + 8, base + 18, &blk[b].col);
     pack_ffn(hw, base + 22, base + 20, &blk[b].ffn);
     pf_pack_ffn_tc(blk[b].ffn, &tc[b]);
+    pf_pack_ffn_tc(blk[b].ffn, &tc16[b], true);
     PfFfnConst kc;
     for (int c = 0; c < PF_D; ++c) {
       for (int hh = 0; hh < PF_H; ++hh) kc.wq[c][hh] = blk[b].col.wqk[4 + hh][c];
@@ -263,11 +265,13 @@ int pf_create(pf_handle* out, const pf_cfg* cfg, const float* const* weights_dev
   if ((e = cudaMalloc(&h->head_dev, sizeof(PfHeadW))) != cudaSuccess ||
       (e = cudaMalloc(&h->blk_dev, sizeof(PfBlockW) * nb)) != cudaSuccess ||
       (e = cudaMalloc(&h->tc_dev, sizeof(PfFfnTcW) * nb)) != cudaSuccess ||
+      (e = cudaMalloc(&h->tc16_dev, sizeof(PfFfnTcW) * nb)) != cudaSuccess ||
       (e = cudaMalloc(&h->err_dev, sizeof(int))) != cudaSuccess ||
       (e = cudaMemset(h->err_dev, 0, sizeof(int))) != cudaSuccess ||
       (e = cudaMemcpy(h->head_dev, head.data(), sizeof(PfHeadW), cudaMemcpyHostToDevice)) != cudaSuccess ||
       (e = cudaMemcpy(h->blk_dev, blk.data(), sizeof(PfBlockW) * nb, cudaMemcpyHostToDevice)) != cudaSuccess ||
-      (e = cudaMemcpy(h->tc_dev, tc.data(), sizeof(PfFfnTcW) * nb, cudaMemcpyHostToDevice)) != cudaSuccess) {
+      (e = cudaMemcpy(h->tc_dev, tc.data(), sizeof(PfFfnTcW) * nb, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(h->tc16_dev, tc16.data(), sizeof(PfFfnTcW) * nb, cudaMemcpyHostToDevice)) != cudaSuccess) {
     cleanup();
     return fail(PF_ERR_CUDA, "pf_create: %s", cudaGetErrorString(e));
   }
@@ -292,6 +296,7 @@ void pf_destroy(pf_handle h) {
   if (h->head_dev) cudaFree(h->head_dev);
   if (h->blk_dev) cudaFree(h->blk_dev);
   if (h->tc_dev) cudaFree(h->tc_dev);
+  if (h->tc16_dev) cudaFree(h->tc16_dev);
   if (h->err_dev) cudaFree(h->err_dev);
   if (h->peers_dev) cudaFree(h->peers_dev);
   for (auto& r : h->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -301,7 +306,7 @@ void pf_destroy(pf_handle h) {
 
 int pf_set_precision(pf_handle h, int precision) {
   if (!h) return fail(PF_ERR_ARG, "pf_set_precision: null handle");
-  if (precision < PF_PREC_FP32 || precision > PF_PREC_BF16) return fail(PF_ERR_ARG, "pf_set_precision: bad mode %d", precision);
+  if (precision < PF_PREC_FP32 || precision > PF_PREC_FP16) return fail(PF_ERR_ARG, "pf_set_precision: bad mode %d", precision);
   h->cfg.precision = precision;
   return PF_OK;
 }
@@ -456,10 +461,14 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
                                                                apply_only ? 1 : 0);
     } else {
       Timed t_(h, PF_KC_FFN, st);
-      const int terms = h->cfg.precision == PF_PREC_BF16 ? 1 : 3;
+      const int prec = h->cfg.precision;
+      const int terms = prec == PF_PREC_BF16 ? 1 : prec == PF_PREC_FP16 ? 2 : 3;
+      const int fmt = prec == PF_PREC_BF16 ? WS_FMT_BF16 : prec == PF_PREC_FP16 ? WS_FMT_F16 : WS_FMT_BF16X3;
+      if (prec == PF_PREC_FP16 && h->ffn_impl != 1)
+        return fail(PF_ERR_ARG, "pf_forward: PF_PREC_FP16 needs the warp-specialised FFN kernel (unset PF_FFN_IMPL)");
       const int rc = h->ffn_impl == 1
-                         ? pf_ffn_ws_launch(h->ffn_const[b], h->tc_dev + b, x, colM, L, (int)pl.Pl, B, h->n_sm, terms,
-                                            h->err_dev, h->dump_dev, h->ws_prof, st)
+                         ? pf_ffn_ws_launch(h->ffn_const[b], (prec == PF_PREC_FP16 ? h->tc16_dev : h->tc_dev) + b, x, colM, L,
+                                            (int)pl.Pl, B, h->n_sm, fmt, terms, h->err_dev, h->dump_dev, h->ws_prof, st)
                          : pf_ffn_tc_launch(&bw->col, h->tc_dev + b, x, colM, L, (int)pl.Pl, n_tok, h->n_sm, terms,
                                             h->err_dev, h->dump_dev, st);
       if (rc != 0) return fail(PF_ERR_CUDA, "pf_forward: tcgen05 FFN launch failed (%d)", rc);

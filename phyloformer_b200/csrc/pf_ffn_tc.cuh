@@ -18,6 +18,7 @@
 // HBM traffic is one fp32 read and one fp32 write of the token (512 B).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "pf_common.cuh"
 
@@ -59,12 +60,28 @@ inline float bf16_to_f32(uint16_t h) {
   return f;
 }
 
-inline void pf_pack_ffn_tc(const PfFfnW& f, PfFfnTcW* o) {
+inline uint16_t f32_to_f16_rn(float f) {   // host: cuda_fp16.h conversions are host-callable
+  const __half h = __float2half_rn(f);
+  uint16_t u;
+  memcpy(&u, &h, 2);
+  return u;
+}
+inline float f16_to_f32(uint16_t u) {
+  __half h;
+  memcpy(&h, &u, 2);
+  return __half2float(h);
+}
+
+// Weight images for the tensor-core FFN: 16-bit hi/lo parts (bf16, or fp16 when `f16`), already in
+// the UMMA shared-memory layout.
+inline void pf_pack_ffn_tc(const PfFfnW& f, PfFfnTcW* o, bool f16 = false) {
+  auto enc = [&](float w) { return f16 ? f32_to_f16_rn(w) : f32_to_bf16_rn(w); };
+  auto dec = [&](uint16_t u) { return f16 ? f16_to_f32(u) : bf16_to_f32(u); };
   for (int n = 0; n < PF_HID; ++n)
     for (int k = 0; k < PF_D; ++k) {
       const float w = f.w1T[k][n];
-      const uint16_t hi = f32_to_bf16_rn(w);
-      const uint16_t lo = f32_to_bf16_rn(w - bf16_to_f32(hi));
+      const uint16_t hi = enc(w);
+      const uint16_t lo = enc(w - dec(hi));
       const uint32_t off = umma_off_k64(n, k) / 2;
       o->w1hi[off] = hi;
       o->w1lo[off] = lo;
@@ -72,8 +89,8 @@ inline void pf_pack_ffn_tc(const PfFfnW& f, PfFfnTcW* o) {
   for (int n = 0; n < PF_D; ++n)
     for (int k = 0; k < PF_HID; ++k) {
       const float w = f.w2T[k][n];
-      const uint16_t hi = f32_to_bf16_rn(w);
-      const uint16_t lo = f32_to_bf16_rn(w - bf16_to_f32(hi));
+      const uint16_t hi = enc(w);
+      const uint16_t lo = enc(w - dec(hi));
       const uint32_t off = umma_off_k256(n, k, PF_D) / 2;
       o->w2hi[off] = hi;
       o->w2lo[off] = lo;
@@ -136,10 +153,10 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-// kind::f16 instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), K-major A and B,
-// N>>3 at bit 17, M>>4 at bit 24.
-__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32 (bit 4), A and B formats at bits 7 and 10 (0 = fp16,
+// 1 = bf16), K-major A and B, N>>3 at bit 17, M>>4 at bit 24.
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N, bool f16 = false) {
+  return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(

@@ -126,6 +126,14 @@ __device__ __forceinline__ u64 gelu_fast2(float h0, float h1) {
   return fma2(pk2(-t0, -t1), pk2(e0, e1), pk2(fmaxf(h0, 0.f), fmaxf(h1, 0.f)));
 }
 
+// Operand formats of the two GEMMs' A operands (template parameter FMT):
+//   WS_FMT_BF16X3  bf16 hi + lo parts (3-term product with the hi/lo weight images)
+//   WS_FMT_BF16    bf16, one rounding, no lo part (fast mode)
+//   WS_FMT_F16     fp16, one rounding, no lo part; the weights keep hi + lo (2-term product)
+#define WS_FMT_BF16X3 0
+#define WS_FMT_BF16 1
+#define WS_FMT_F16 2
+
 // bf16 hi/lo split of a packed pair: hi = rn(g), lo = rn(g - hi); both as packed bf16x2 words.
 __device__ __forceinline__ void split2(u64 g, uint32_t& hi, uint32_t& lo) {
 #ifdef WS_DIAG_NO_SPLIT  // timing diagnostic only (wrong results)
@@ -141,6 +149,23 @@ __device__ __forceinline__ void split2(u64 g, uint32_t& hi, uint32_t& lo) {
   const __nv_bfloat162 ll = __floats2bfloat162_rn(l0, l1);
   lo = *reinterpret_cast<const uint32_t*>(&ll);
 }
+// One packed pair -> the 16-bit operand word(s) of format FMT (lo is written only for BF16X3).
+template <int FMT>
+__device__ __forceinline__ void cvt2(u64 g, uint32_t& hi, uint32_t& lo) {
+  if (FMT == WS_FMT_BF16X3) {
+    split2(g, hi, lo);
+  } else {
+    float g0, g1;
+    up2(g, g0, g1);
+    if (FMT == WS_FMT_F16) {
+      const __half2 hh = __floats2half2_rn(g0, g1);
+      hi = *reinterpret_cast<const uint32_t*>(&hh);
+    } else {
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(g0, g1);
+      hi = *reinterpret_cast<const uint32_t*>(&hh);
+    }
+  }
+}
 
 struct WsTileMap {  // tile index -> rows
   int L, Pl, nW, nPG;
@@ -152,7 +177,7 @@ struct WsTileMap {  // tile index -> rows
   }
 };
 
-template <bool PROF>
+template <bool PROF, int FMT>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restrict__ Wt, float* __restrict__ x,
                   const float* __restrict__ colM, int L, int Pl, int B, int n_terms, int* __restrict__ err_flag,
@@ -372,11 +397,11 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const u64 nv = mul2(add2(pk2(xr[8 * cl + 2 * i], xr[8 * cl + 2 * i + 1]), nm), rs);
-              split2(nv, hi[i], lo[i]);
+              cvt2<FMT>(nv, hi[i], lo[i]);
             }
             const uint32_t off = rowoff + (uint32_t)(((ch ^ r) & 7) << 4);
             *reinterpret_cast<uint4*>(a1hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(a1lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            if (FMT == WS_FMT_BF16X3) *reinterpret_cast<uint4*>(a1lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
         }
         { const long long t0 = TIC(); tc_wait_st(); TOC(3, t0); }
@@ -526,11 +551,11 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const u64 nv = mul2(add2(pk2(xr[8 * ch + 2 * i], xr[8 * ch + 2 * i + 1]), nm), rs);
-            split2(nv, hi[i], lo[i]);
+            cvt2<FMT>(nv, hi[i], lo[i]);
           }
           const uint32_t off = rowoff + (uint32_t)(((ch ^ r) & 7) << 4);
           *reinterpret_cast<uint4*>(a1hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(a1lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          if (FMT == WS_FMT_BF16X3) *reinterpret_cast<uint4*>(a1lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
       }
       { const long long t0 = TIC(); tc_wait_st(); TOC(3, t0); }
@@ -599,7 +624,7 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
     // The whole warp walks the loop (so descriptors live in uniform registers); one elected lane
     // issues.  Descriptors are built once: per k-step only the 16-byte-unit address field moves.
     if (n_my > 0) {
-      const uint32_t idesc1 = umma_idesc(128, 128), idesc2 = umma_idesc(128, 64);
+      const uint32_t idesc1 = umma_idesc(128, 128, FMT == WS_FMT_F16), idesc2 = umma_idesc(128, 64, FMT == WS_FMT_F16);
       const u64 dA00 = umma_desc(sbase + WS_OFF_A1), dA01 = umma_desc(sbase + WS_OFF_A1 + 16384);
       const u64 dW1h = umma_desc(sbase + TC_OFF_W1HI), dW1l = umma_desc(sbase + TC_OFF_W1LO);
       const u64 dW2h = umma_desc(sbase + TC_OFF_W2HI), dW2l = umma_desc(sbase + TC_OFF_W2LO);
@@ -623,8 +648,8 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
           if (t < n_terms) {
-            const u64 db = (t == 2) ? dW2l : dW2h;
-            const uint32_t a_sel = (t == 1) ? 8u : 0u;
+            const u64 db = (t == 1) ? dW2l : dW2h;        // same term order as GEMM1: hi.hi, hi.lo(W), lo(A).hi
+            const uint32_t a_sel = (t == 2) ? 8u : 0u;
 #pragma unroll
             for (int s8 = 0; s8 < 8; ++s8) {
               const int s = half * 8 + s8;
@@ -691,10 +716,10 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
           float h0, h1;   // one packed add for the pair's bias
           up2(add2(pk2(__uint_as_float(vc[2 * i]), __uint_as_float(vc[2 * i + 1])),
                    *reinterpret_cast<const u64*>(sb1 + cc + 2 * i)), h0, h1);
-          split2(gelu_fast2(h0, h1), hi[i], lo[i]);
+          cvt2<FMT>(gelu_fast2(h0, h1), hi[i], lo[i]);
         }
         tmem_st8(tmem + lane_base + cc, hi);
-        tmem_st8(tmem + lane_base + cc + 8, lo);
+        if (FMT == WS_FMT_BF16X3) tmem_st8(tmem + lane_base + cc + 8, lo);
       };
       const int n_mine = (8 - chf + WS_NCG - 1) / WS_NCG;   // chunks of this warp in a half
       tmem_ld16(tmem + lane_base + col_of(0), v[0]);
@@ -796,19 +821,28 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
 }
 
 inline int pf_ffn_ws_init() {
-  int rc = (int)cudaFuncSetAttribute(k_colapply_ffn_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
-  if (rc == 0) rc = (int)cudaFuncSetAttribute(k_colapply_ffn_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
+  int rc = (int)cudaFuncSetAttribute(k_colapply_ffn_ws<false, WS_FMT_BF16X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
+  if (rc == 0) rc = (int)cudaFuncSetAttribute(k_colapply_ffn_ws<true, WS_FMT_BF16X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
+  if (rc == 0) rc = (int)cudaFuncSetAttribute(k_colapply_ffn_ws<false, WS_FMT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
+  if (rc == 0) rc = (int)cudaFuncSetAttribute(k_colapply_ffn_ws<false, WS_FMT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
   return rc;
 }
 
+// fmt: WS_FMT_*; n_terms: MMA passes per product (3 for BF16X3, 1 for BF16, 2 for F16 = hi and lo weights).
+// Wt must hold the weight images of the matching 16-bit format.
 inline int pf_ffn_ws_launch(const PfFfnConst& kc, const PfFfnTcW* Wt, float* x, const float* colM, int L, int Pl, int B,
-                            int n_sm, int n_terms, int* err_flag, float* dump, int prof, cudaStream_t st) {
+                            int n_sm, int fmt, int n_terms, int* err_flag, float* dump, int prof, cudaStream_t st) {
   const long long nt = (long long)B * ((L + WS_S - 1) / WS_S) * ((Pl + WS_G - 1) / WS_G);
   if (nt > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
+  if (fmt != WS_FMT_BF16X3 && n_terms > 2) return (int)cudaErrorInvalidValue;   // no lo activations in these formats
   const int grid = (int)(nt < n_sm ? nt : n_sm);
-  if (prof || dump != nullptr)   // the debug/profiling instantiation carries the dump and the role timers
-    k_colapply_ffn_ws<true><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(kc, Wt, x, colM, L, Pl, B, n_terms, err_flag, dump);
+  if (fmt == WS_FMT_F16)
+    k_colapply_ffn_ws<false, WS_FMT_F16><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(kc, Wt, x, colM, L, Pl, B, n_terms, err_flag, nullptr);
+  else if (fmt == WS_FMT_BF16)
+    k_colapply_ffn_ws<false, WS_FMT_BF16><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(kc, Wt, x, colM, L, Pl, B, n_terms, err_flag, nullptr);
+  else if (prof || dump != nullptr)   // the debug/profiling instantiation carries the dump and the role timers
+    k_colapply_ffn_ws<true, WS_FMT_BF16X3><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(kc, Wt, x, colM, L, Pl, B, n_terms, err_flag, dump);
   else
-    k_colapply_ffn_ws<false><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(kc, Wt, x, colM, L, Pl, B, n_terms, err_flag, dump);
+    k_colapply_ffn_ws<false, WS_FMT_BF16X3><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(kc, Wt, x, colM, L, Pl, B, n_terms, err_flag, dump);
   return (int)cudaGetLastError();
 }

@@ -148,7 +148,7 @@ class Phyloformer(nn.Module):
             pass
 
     def set_precision(self, precision: str):
-        """'fp32' (FFMA, ~1e-6 of the reference), 'bf16x3' (tcgen05, 3-term split) or 'bf16'."""
+        """'fp32' (FFMA, ~1e-6 of the reference), 'bf16x3' (tcgen05, 3-term split), or the fast modes 'fp16' / 'bf16' (no activation split)."""
         if precision not in _cabi.PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_cabi.PRECISIONS)}")
         self.precision = precision
