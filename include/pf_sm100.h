@@ -42,6 +42,9 @@ extern "C" {
 #define PF_ERR_WORKSPACE  -3
 #define PF_ERR_NO_DEVICE  -4 /* no sm_100 device: there is no CPU fallback */
 #define PF_ERR_REDUCE     -5
+#define PF_ERR_FASTA_RESIDUE  -10 /* residue outside ALPHABET: the reference raises KeyError (data.py:26) */
+#define PF_ERR_FASTA_RAGGED   -11 /* unequal sequence lengths: the reference's torch.tensor() raises ValueError */
+#define PF_ERR_FASTA_NOHEADER -12 /* sequence data before the first '>' (reference: IndexError, data.py:26)  */
 
 /* number of fp32 values exchanged per (MSA, site) per block between pair shards:
  * sum_p k~ (4), sum_p q~ (4), sum_p k~ * v (64)    (attention.py:179-190 before normalising) */
@@ -110,6 +113,25 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
 /* Replaces infer_alns.py:14-25 (vec_to_phylip's triu scatter + dm + dm.T):
  * (B,P) distances -> (B,n,n) symmetric matrices with a zero diagonal. */
 int pf_dist_to_matrix(const float* dist_dev, int B, int n, float* mat_dev, void* stream);
+
+/* Replaces the parsing half of phyloformer/data.py:11-27 (load_alignment): host-only, no device
+ * work.  `text[0..len)` is the FASTA file.  Lines are stripped like bytes.strip(); a line that
+ * starts with '>' opens a record, every other non-empty line is residues.  Writes the residue
+ * codes (index in ALPHABET = "ARNDCQEGHILKMFPSTWYVX-") row-major (n, L) into codes[0..cap), the
+ * alignment length into *L_out and the byte range of every record name (text after '>') into
+ * name_off/name_len (at most max_names).  Returns n, or PF_ERR_FASTA_* / PF_ERR_ARG; on
+ * PF_ERR_FASTA_RESIDUE *bad_char holds the offending byte. */
+long long pf_parse_fasta(const char* text, long long len, uint8_t* codes, long long cap,
+                         int32_t* L_out, int64_t* name_off, int32_t* name_len, int32_t max_names,
+                         int32_t* bad_char);
+
+/* Replaces the text half of infer_alns.py:19-23 (vec_to_phylip): host-only, no device work.
+ * Writes "n\n" and one line per taxon, "name v v ... v\n" with every value as "%.10f" (same
+ * digits as the reference's f"{x:.10f}"), into out[0..cap).  dm_host is the (n,n) fp32 matrix in
+ * host memory, names are NUL-terminated UTF-8.  Returns the text length in bytes (call again
+ * with a larger buffer if it exceeds cap; nothing is NUL-terminated), or a negative PF_ERR_*. */
+long long pf_format_phylip(const float* dm_host, int n, const char* const* names, char* out,
+                           long long cap);
 
 /* Kernel launches enqueued by the last pf_forward on this handle (for bench.py's
  * gpu_launches claim). */

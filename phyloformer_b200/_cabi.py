@@ -11,6 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PF_LIB", os.path.join(HERE, "libpf_sm100.so"))  # PF_LIB: A/B-test another build
 
 PF_ABI_VERSION = 1
+PF_ERR_FASTA_RESIDUE, PF_ERR_FASTA_RAGGED, PF_ERR_FASTA_NOHEADER = -10, -11, -12
 PF_PREC_FP32, PF_PREC_BF16X3, PF_PREC_BF16, PF_PREC_FP16 = 0, 1, 2, 3
 PRECISIONS = {"fp32": PF_PREC_FP32, "bf16x3": PF_PREC_BF16X3, "bf16": PF_PREC_BF16, "fp16": PF_PREC_FP16}
 PF_COLSUM_FLOATS = 72
@@ -38,6 +39,9 @@ SYMBOLS = {
     "pf_forward_debug": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64,
                                  c_void_p, c_void_p, c_size_t, c_void_p, REDUCE_FN, c_void_p, c_int, c_void_p]),
     "pf_dist_to_matrix": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "pf_parse_fasta": (ctypes.c_longlong, [c_char_p, ctypes.c_longlong, c_void_p, ctypes.c_longlong, POINTER(c_int32),
+                                           c_void_p, c_void_p, c_int32, POINTER(c_int32)]),
+    "pf_format_phylip": (ctypes.c_longlong, [c_void_p, c_int, POINTER(c_char_p), c_char_p, ctypes.c_longlong]),
     "pf_last_launch_count": (c_int, [c_void_p]),
     "pf_set_peer_exchange": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p), c_size_t]),
     "pf_peer_exchange_bytes": (c_size_t, [c_size_t]),

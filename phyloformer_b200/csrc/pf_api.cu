@@ -503,6 +503,114 @@ int pf_dist_to_matrix(const float* dist_dev, int B, int n, float* mat_dev, void*
   return PF_OK;
 }
 
+// ---- host-side FASTA parse (no device work) ---------------------------------------------------
+static inline bool is_space(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13); }   // bytes.strip() set
+
+long long pf_parse_fasta(const char* text, long long len, uint8_t* codes, long long cap, int32_t* L_out,
+                         int64_t* name_off, int32_t* name_len, int32_t max_names, int32_t* bad_char) {
+  if (!text || len < 0 || !codes || !L_out || !name_off || !name_len)
+    return (long long)fail(PF_ERR_ARG, "pf_parse_fasta: null argument");
+  static const char alphabet[] = "ARNDCQEGHILKMFPSTWYVX-";   // reference data.py:7
+  uint8_t lut[256];
+  memset(lut, 255, sizeof(lut));
+  for (int i = 0; alphabet[i]; ++i) lut[(unsigned char)alphabet[i]] = (uint8_t)i;
+  long long n = 0, pos = 0, cur_len = 0, L = -1;
+  bool ragged = false;
+  auto close_record = [&]() {
+    if (n == 0) return;
+    if (L < 0) L = cur_len; else if (cur_len != L) ragged = true;
+  };
+  long long i = 0;
+  while (i < len) {
+    long long e = i;
+    while (e < len && text[e] != '\n') ++e;
+    long long a = i, b = e;                      // strip the line like bytes.strip()
+    while (a < b && is_space((unsigned char)text[a])) ++a;
+    while (b > a && is_space((unsigned char)text[b - 1])) --b;
+    if (a < b && text[a] == '>') {
+      close_record();
+      if (n >= max_names) return (long long)fail(PF_ERR_ARG, "pf_parse_fasta: more than %d records", max_names);
+      name_off[n] = a + 1;
+      name_len[n] = (int32_t)(b - a - 1);
+      ++n;
+      cur_len = 0;
+    } else if (a < b) {
+      if (n == 0) return (long long)fail(PF_ERR_FASTA_NOHEADER, "pf_parse_fasta: sequence data before the first '>' header");
+      for (long long k = a; k < b; ++k) {
+        const uint8_t c = lut[(unsigned char)text[k]];
+        if (c == 255) {
+          if (bad_char) *bad_char = (unsigned char)text[k];
+          return (long long)fail(PF_ERR_FASTA_RESIDUE, "pf_parse_fasta: residue 0x%02x outside the alphabet", (unsigned char)text[k]);
+        }
+        if (pos >= cap) return (long long)fail(PF_ERR_ARG, "pf_parse_fasta: code buffer too small");
+        codes[pos++] = c;
+      }
+      cur_len += b - a;
+    }
+    i = e + 1;
+  }
+  close_record();
+  if (ragged) return (long long)fail(PF_ERR_FASTA_RAGGED, "pf_parse_fasta: sequences have different lengths");
+  *L_out = (int32_t)(L < 0 ? 0 : L);
+  return n;
+}
+
+// ---- host-side PHYLIP text (no device work) --------------------------------------------------
+// "%.10f" of a float, exactly as printf / Python format it (correctly rounded, ties to even),
+// through integer arithmetic: f = mant * 2^e, so round(f * 10^10) = round(mant * 10^10 / 2^-e).
+static inline int fmt_fixed10(float f, char* out) {
+  uint32_t bits;
+  memcpy(&bits, &f, 4);
+  const uint32_t ex = (bits >> 23) & 0xffu;
+  if ((bits >> 31) || ex == 0xffu || f >= 1.0e6f) {   // negative, inf/nan or huge: libc path
+    const double d = (double)f;
+    if (d != d) { memcpy(out, "nan", 3); return 3; }   // Python prints nan / inf / -inf
+    return snprintf(out, 64, "%.10f", d);
+  }
+  const uint32_t mant = (bits & 0x7fffffu) | (ex ? 0x800000u : 0u);
+  const int shift = 150 - (int)(ex ? ex : 1u);          // f = mant * 2^-shift, shift in [5, 149] here
+  unsigned long long q = 0;
+  if (shift < 100) {
+    const unsigned __int128 num = (unsigned __int128)mant * 10000000000ULL;   // < 2^58
+    const unsigned __int128 one = 1;
+    q = (unsigned long long)(num >> shift);
+    const unsigned __int128 rem = num & ((one << shift) - 1), half = one << (shift - 1);
+    if (rem > half || (rem == half && (q & 1ULL))) ++q;
+  }
+  const unsigned long long ip = q / 10000000000ULL, fp = q % 10000000000ULL;
+  char tmp[24];
+  int ni = 0;
+  unsigned long long t = ip;
+  do { tmp[ni++] = (char)('0' + t % 10); t /= 10; } while (t);
+  int k = 0;
+  while (ni) out[k++] = tmp[--ni];
+  out[k++] = '.';
+  unsigned long long r = fp;
+  for (int dgt = 9; dgt >= 0; --dgt) { out[k + dgt] = (char)('0' + r % 10); r /= 10; }
+  return k + 10;
+}
+
+long long pf_format_phylip(const float* dm_host, int n, const char* const* names, char* out, long long cap) {
+  if (!dm_host || !names || n < 1 || (cap > 0 && !out)) return (long long)fail(PF_ERR_ARG, "pf_format_phylip: bad argument");
+  long long pos = 0;
+  char num[80];
+  auto put = [&](const char* src, size_t len) {
+    if (pos + (long long)len <= cap) memcpy(out + pos, src, len);
+    pos += (long long)len;
+  };
+  put(num, (size_t)snprintf(num, sizeof(num), "%d\n", n));
+  for (int i = 0; i < n; ++i) {
+    if (!names[i]) return (long long)fail(PF_ERR_ARG, "pf_format_phylip: null name %d", i);
+    put(names[i], strlen(names[i]));
+    for (int j = 0; j < n; ++j) {
+      num[0] = ' ';
+      put(num, (size_t)(1 + fmt_fixed10(dm_host[(size_t)i * n + j], num + 1)));
+    }
+    put("\n", 1);
+  }
+  return pos;   // bytes of text; the caller retries with a larger buffer if this exceeds cap
+}
+
 int pf_last_launch_count(pf_handle h) { return h ? h->launches : 0; }
 
 int pf_set_peer_exchange(pf_handle h, int rank, int world, void* const* peer_bufs_host, size_t slot_floats) {

@@ -16,8 +16,39 @@ for _i, _c in enumerate(ALPHABET):
 
 
 def load_alignment_idx(filepath):
-    """Returns ((n, L) uint8 tensor of residue codes, ids). KeyError on a residue outside
-    ALPHABET, like the reference (data.py:26)."""
+    """Returns ((n, L) uint8 tensor of residue codes, ids).  Same errors as the reference:
+    KeyError(byte) on a residue outside ALPHABET (data.py:26), ValueError for sequences of
+    different lengths (the reference's torch.tensor() on ragged lists), IndexError for residues
+    before the first header.  The parse itself is the library's host-side pf_parse_fasta (one C
+    pass over the file, no GIL, so the CLI's parse pool really runs in parallel)."""
+    import ctypes
+    from . import _cabi
+    with open(filepath, "rb") as aln:
+        text = aln.read()
+    lib = _cabi.load()
+    max_names = text.count(b">") + 1
+    codes = np.empty(max(len(text), 1), dtype=np.uint8)
+    off = np.empty(max_names, dtype=np.int64)
+    ln = np.empty(max_names, dtype=np.int32)
+    L, bad = ctypes.c_int32(0), ctypes.c_int32(0)
+    n = lib.pf_parse_fasta(text, len(text), codes.ctypes.data, codes.size, ctypes.byref(L), off.ctypes.data,
+                           ln.ctypes.data, max_names, ctypes.byref(bad))
+    if n == _cabi.PF_ERR_FASTA_RESIDUE:
+        raise KeyError(bad.value)
+    if n == _cabi.PF_ERR_FASTA_RAGGED:
+        raise ValueError(f"{filepath}: sequences have different lengths")
+    if n == _cabi.PF_ERR_FASTA_NOHEADER:
+        raise IndexError(f"{filepath}: sequence data before the first '>' header")
+    if n < 0:
+        raise _cabi.PfError(lib.pf_last_error().decode())
+    ids = [text[o:o + k].decode("utf8") for o, k in zip(off[:n].tolist(), ln[:n].tolist())]
+    if n == 0:
+        return torch.zeros((0, 0), dtype=torch.uint8), ids
+    return torch.from_numpy(codes[: n * L.value].reshape(n, L.value).copy()), ids
+
+
+def _load_alignment_idx_py(filepath):
+    """Pure-Python restatement of the same parse (tests cross-check the C parser against it)."""
     ids, seqs, cur = [], [], None
     with open(filepath, "rb") as aln:
         for line in aln:
@@ -27,6 +58,8 @@ def load_alignment_idx(filepath):
                 cur = []
                 seqs.append(cur)
             elif line:
+                if cur is None:
+                    raise IndexError(f"{filepath}: sequence data before the first '>' header")
                 cur.append(line)
     rows = []
     for parts in seqs:
@@ -34,7 +67,7 @@ def load_alignment_idx(filepath):
         codes = _LUT[raw]
         bad = np.nonzero(codes == 255)[0]
         if bad.size:
-            raise KeyError(chr(int(raw[bad[0]])))   # same key the reference's LOOKUP[char] raises
+            raise KeyError(int(raw[bad[0]]))   # the reference's LOOKUP has integer (byte) keys
         rows.append(codes)
     if len({len(r) for r in rows}) > 1:
         raise ValueError(f"{filepath}: sequences have different lengths")

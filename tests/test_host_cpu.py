@@ -85,6 +85,40 @@ def test_load_alignment_errors(tmp_path):
     p.write_text(">a\nAC\nDE\n>b\nAC-X\n")         # multi-line records, gap and X
     idx, ids = load_alignment_idx(str(p))
     assert ids == ["a", "b"] and idx.tolist() == [[0, 4, 3, 6], [0, 4, 21, 20]]
+    p.write_text(">a\nACDZ\n")
+    with pytest.raises(KeyError) as ei:              # the reference's LOOKUP has integer (byte) keys
+        load_alignment_idx(str(p))
+    assert ei.value.args == (ord("Z"),)
+    p.write_text("ACD\n>a\nACD\n")
+    with pytest.raises(IndexError):                  # reference: sequences[-1] on an empty list
+        load_alignment_idx(str(p))
+
+
+def test_c_fasta_parser_matches_python_restatement(tmp_path):
+    """pf_parse_fasta (host-only C-ABI entry) against the pure-Python parse on awkward files:
+    CRLF, blank lines, surrounding whitespace, wrapped records, no trailing newline, spaces in
+    names, an empty file, and every committed test alignment."""
+    from phyloformer_b200.data import _load_alignment_idx_py, load_alignment_idx
+    from tests._util import list_stems
+    cases = [
+        b">a\r\nACDE\r\n>b\r\nAC-X\r\n",
+        b"\n\n>a b c  \n  ACDE  \n\n>  spaced name\nAC\n\nDE",
+        b">only\nARNDCQEGHILKMFPSTWYVX-",
+        b">x\n>y\n",
+        b"",
+        b">a\tb\nAC\tDE\n".replace(b"AC\tDE", b"ACDE"),
+    ]
+    for k, data in enumerate(cases):
+        p = tmp_path / f"c{k}.fa"
+        p.write_bytes(data)
+        a, ia = load_alignment_idx(str(p))
+        b, ib = _load_alignment_idx_py(str(p))
+        assert ia == ib and a.shape == b.shape and torch.equal(a, b), (k, ia, ib)
+    for stem in list_stems():
+        f = os.path.join(GOLDEN, "msas", stem + ".fa")
+        a, ia = load_alignment_idx(f)
+        b, ib = _load_alignment_idx_py(f)
+        assert ia == ib and torch.equal(a, b)
 
 
 def test_phylip_text_matches_reference(ref_testdata):
@@ -119,3 +153,34 @@ def test_pair_sharding_arithmetic():
             sizes = [hi - lo for lo, hi in r]
             assert max(sizes) - min(sizes) <= 1
     assert sh.batch_range(256, 3, 8) == (96, 128)
+
+
+def test_phylip_formatter_matches_python_digits():
+    """pf_format_phylip (host-only C-ABI entry) must print exactly what the reference's
+    f"{x:.10f}" prints (infer_alns.py:21): ties, tiny, subnormal, large and negative values,
+    random bit patterns, and a full matrix against the pure-Python text."""
+    import ctypes
+    import numpy as np
+    import infer_alns
+    from phyloformer_b200 import _cabi
+    lib = _cabi.load()
+    rng = np.random.default_rng(3)
+    special = np.array([0.0, 1.0, 0.5, 0.25, 2.5e-11, 5e-11, 7.5e-11, 1e-10, 1.5e-10, 0.1, 0.3, 1 / 3,
+                        1e-45, 1e-38, 3.4e38, 999999.9, 1e6, 123456.789, -0.25, -1e-12, 2 ** -34, 3 * 2 ** -35,
+                        np.float32(0.99999999995), 12.3456789012, np.nan, np.inf, -np.inf], dtype=np.float32)
+    bits = rng.integers(0, 0x4B000000, size=4000, dtype=np.uint32).view(np.float32)   # [0, 8.4e6)
+    small = (rng.random(4000) * 3).astype(np.float32)
+    vals = np.concatenate([special, bits, small]).astype(np.float32)
+    n = 90
+    vals = np.resize(vals, n * n).reshape(n, n)
+    ids = [f"taxon_{i}" for i in range(n)]
+    names = (ctypes.c_char_p * n)(*[i.encode() for i in ids])
+    cap = 8
+    need = lib.pf_format_phylip(vals.ctypes.data, n, names, ctypes.create_string_buffer(cap), cap)
+    assert need > cap                                  # too small: reports the size it needs
+    buf = ctypes.create_string_buffer(need)
+    assert lib.pf_format_phylip(vals.ctypes.data, n, names, buf, need) == need
+    want = f"{n}\n" + "".join(f"{i} " + " ".join("%.10f" % float(v) for v in row) + "\n" for i, row in zip(ids, vals))
+    assert buf.raw[:need].decode() == want
+    assert infer_alns.matrix_to_phylip(vals, ids) == want
+    assert lib.pf_format_phylip(None, n, names, buf, need) < 0
