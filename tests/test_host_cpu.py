@@ -184,3 +184,16 @@ def test_phylip_formatter_matches_python_digits():
     assert buf.raw[:need].decode() == want
     assert infer_alns.matrix_to_phylip(vals, ids) == want
     assert lib.pf_format_phylip(None, n, names, buf, need) < 0
+
+
+def test_header_is_valid_c99_and_demo_compiles(tmp_path):
+    """include/pf_sm100.h must be consumable from plain C (the boundary has no C++ or torch types):
+    compile the C caller used by the GPU test with -std=c99 -Wall -Werror (no link, no GPU)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None or not os.path.isdir("/usr/local/cuda/include"):
+        pytest.skip("gcc / CUDA headers not available")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    "-I", "/usr/local/cuda/include", "-c", os.path.join(ROOT, "tests", "cabi", "cabi_demo.c"),
+                    "-o", str(tmp_path / "cabi_demo.o")], check=True)
