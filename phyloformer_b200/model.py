@@ -177,6 +177,11 @@ class Phyloformer(nn.Module):
         self._peer_failed = False
         return self
 
+    def unshard(self):
+        """Back to one rank computing every pair (undoes shard_pairs)."""
+        self._shard = None
+        return self
+
     def _setup_peer_exchange(self, lib, need_floats, device):
         """(Re)allocate the symmetric exchange buffer; collective over the shard group."""
         import torch.distributed as dist
