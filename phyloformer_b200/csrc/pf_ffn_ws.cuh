@@ -23,7 +23,6 @@
 //   MMA order      G2a(i)  G1a(i+1)  G2b(i)  G1b(i+1)        (in-order issue covers the WAR on D1)
 //   epilogue order E1a(i)  E2(i-1)  E1b(i)
 #pragma once
-#include <type_traits>
 
 #include "pf_ffn_tc.cuh"
 
@@ -33,27 +32,13 @@
 #ifndef WS_EW
 #define WS_EW 8
 #endif
-// WS_STORE_WARPS = 1: the final rows (TMEM -> HBM) are stored by the four warps of the MMA warpgroup
-// (the issuer between its issue steps, and its three otherwise idle siblings) instead of the
-// epilogue warps, which are the critical role.
-#ifndef WS_STORE_WARPS
-#define WS_STORE_WARPS 0   // measured: no difference (35.5 ms either way); only valid with WS_EW == 8
-#endif
+// Variants that were built, measured and removed again (DESIGN.md section 3.1 has the numbers):
+// final-row stores by the MMA warpgroup's idle warps, two producer threads per token row
+// (8 producer warps), epilogue warps above the producer in warp-id order.
 #define WS_NCG (WS_EW / 4)            // epilogue column groups per TMEM lane quadrant
-// WS_PSPLIT = 1: every token row is produced by TWO threads (channels 0-31 / 32-63) in two warps of
-// the same TMEM lane quadrant, which exchange their LayerNorm / dot-product partial sums through
-// shared memory: 8 producer warps, half the serial work per thread.
-#ifndef WS_PSPLIT
-#define WS_PSPLIT 0   // measured slower (38-41 vs 36 ms per forward): kept as an experiment
-#endif
-#define WS_NPW (WS_PSPLIT ? 8 : 4)    // producer warps
-// WS_E_HIGH = 1 puts the epilogue warps ABOVE the producer warps in warp-id order (the arbiter
-// favours high warp ids): the epilogue is the critical role.
-#ifndef WS_E_HIGH
-#define WS_E_HIGH 0     // no measurable difference with 4 producer warps
-#endif
-#define WS_PW0 (WS_E_HIGH ? 0 : WS_EW)            // first producer warp
-#define WS_EW0 (WS_E_HIGH ? WS_NPW : 0)           // first epilogue warp
+#define WS_NPW 4                      // producer warps
+#define WS_PW0 WS_EW                  // first producer warp
+#define WS_EW0 0                      // first epilogue warp
 #define WS_MW (WS_EW + WS_NPW)        // MMA warp (highest warp ids: highest issue priority)
 #define WS_THREADS ((WS_EW + WS_NPW + 4) * 32)
 #define WS_G 8    // pairs per tile
@@ -63,7 +48,7 @@
 #define WS_OFF_XST 163840           // [128] rows prefetched with cp.async one tile ahead
 #define WS_OFF_MWIN 198656          // [16][260] floats
 #define WS_MWIN_BYTES (WS_S * PF_MROW * 4)
-#define WS_OFF_XCH (WS_OFF_MWIN + 16896)  // [2 halves][128 rows][8] floats: producer half-row exchange
+#define WS_OFF_XCH (WS_OFF_MWIN + 16896)  // 8 KB, unused (kept so the offsets below do not move)
 #define WS_OFF_B1 (WS_OFF_XCH + 8192)     // [256]
 #define WS_OFF_BAR (WS_OFF_B1 + 1024)     // 14 mbarriers
 #define WS_OFF_TMEM (WS_OFF_BAR + 112)
@@ -205,8 +190,8 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
   if (tid == 0) {
     mbar_init(BAR(0), WS_NPW * 32); mbar_init(BAR(1), WS_NPW * 32);
     mbar_init(BAR(2), 1);   mbar_init(BAR(3), 1);
-    mbar_init(BAR(4), WS_STORE_WARPS ? 128 : WS_EW * 32); mbar_init(BAR(5), WS_STORE_WARPS ? 128 : WS_EW * 32);
-    mbar_init(BAR(6), WS_STORE_WARPS ? 128 : WS_EW * 32);
+    mbar_init(BAR(4), WS_EW * 32); mbar_init(BAR(5), WS_EW * 32);
+    mbar_init(BAR(6), WS_EW * 32);
     mbar_init(BAR(7), 1);   mbar_init(BAR(8), 1);
     mbar_init(BAR(9), WS_EW * 32); mbar_init(BAR(10), WS_EW * 32);
     mbar_init(BAR(11), 1);  mbar_init(BAR(12), 1);  mbar_init(BAR(13), 1);
@@ -244,176 +229,6 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
     }
   };
 
-#if WS_PSPLIT
-  if (warp >= WS_PW0 && warp < WS_PW0 + WS_NPW) {
-    // =============================== PRODUCER (two threads per row) =========================
-    const int pw = warp - WS_PW0;            // 0..7
-    const int q = pw & 3;                    // TMEM lane quadrant (== warp id % 4)
-    const int r = q * 32 + lane;             // row == TMEM lane
-    const int g = r >> 4, s = r & 15;
-    const int ptid = tid - WS_PW0 * 32;      // 0..255
-    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    float* xch = reinterpret_cast<float*>(sm + WS_OFF_XCH);
-    auto body = [&](auto HFC) {
-      constexpr int HF = decltype(HFC)::value;   // channel half: [32 HF, 32 HF + 32)
-      constexpr int C0 = 32 * HF;
-      float* mine_x = xch + (HF * 128 + r) * 8;
-      const float* peer_x = xch + ((HF ^ 1) * 128 + r) * 8;
-      auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory"); };  // the row's two warps
-      int cur_b = -1, cur_w = -1;
-      int b, w, pg;
-      tm.decode((unsigned)t_begin, b, w, pg);
-      const uint32_t xst_u32 = sbase + WS_OFF_XST + (uint32_t)r * WS_XROW + C0 * 4;
-      auto prefetch_row = [&](size_t tok) {  // 8 x 16-byte cp.async: this thread's half row
-        const float* src = x + tok * PF_D + C0;
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(xst_u32 + 16 * c), "l"(src + 4 * c) : "memory");
-      };
-      if (n_my > 0) {
-        const int pair0 = pg * WS_G + g, site0 = w * WS_S + s;
-        if (pair0 < Pl && site0 < L) prefetch_row(((size_t)b * Pl + pair0) * L + site0);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-      }
-      for (int it = 0; it < n_my; ++it) {
-        const uint32_t par = (uint32_t)(it & 1);
-        if (it > 0 && ++pg == tm.nPG) { pg = 0; if (++w == tm.nW) { w = 0; ++b; } }
-        const int pair = pg * WS_G + g, site = w * WS_S + s;
-        const bool valid = (pair < Pl) && (site < L);
-        float xr[32];
-        {
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
-          const float4* srow = reinterpret_cast<const float4*>(sm + WS_OFF_XST + r * WS_XROW + C0 * 4);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) v = srow[c];
-            xr[4 * c] = v.x; xr[4 * c + 1] = v.y; xr[4 * c + 2] = v.z; xr[4 * c + 3] = v.w;
-          }
-          if (it + 1 < n_my) {
-            int nb = b, nw = w, npg = pg + 1;
-            if (npg == tm.nPG) { npg = 0; if (++nw == tm.nW) { nw = 0; ++nb; } }
-            const int npair = npg * WS_G + g, nsite = nw * WS_S + s;
-            if (npair < Pl && nsite < L) prefetch_row(((size_t)nb * Pl + npair) * L + nsite);
-          }
-          asm volatile("cp.async.commit_group;" ::: "memory");
-        }
-        if (b != cur_b || w != cur_w) {  // new site window: reload M_l (all producer warps)
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          const int n_sites = min(WS_S, L - w * WS_S);
-          const float4* src = reinterpret_cast<const float4*>(colM + ((size_t)b * L + (size_t)w * WS_S) * PF_MROW);
-          float4* dst = reinterpret_cast<float4*>(mwin);
-          for (int i = ptid; i < n_sites * (PF_MROW / 4); i += 256) dst[i] = src[i];
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          cur_b = b; cur_w = w;
-        }
-        const float* mrow = mwin + (valid ? s : 0) * PF_MROW;
-        const long long tp0 = TIC();
-        // ---- LN_col statistics and q dots: half-row partials, exchanged with the peer thread ----
-        float mean, rstd;
-        float qh[PF_H];
-        {
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-          for (int c = 0; c < 32; c += 4) { s0 += xr[c]; s1 += xr[c + 1]; s2 += xr[c + 2]; s3 += xr[c + 3]; }
-          const float ps = (s0 + s1) + (s2 + s3);
-          mine_x[0] = ps;
-          pair_sync();
-          mean = (ps + peer_x[0]) * (1.0f / PF_D);
-          float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-          float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-#pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float d = xr[c + k] - mean;
-              d0 = fmaf(kc.wq[C0 + c + k][0], d, d0); d1 = fmaf(kc.wq[C0 + c + k][1], d, d1);
-              d2 = fmaf(kc.wq[C0 + c + k][2], d, d2); d3 = fmaf(kc.wq[C0 + c + k][3], d, d3);
-              if (k == 0) q0 = fmaf(d, d, q0); else if (k == 1) q1 = fmaf(d, d, q1);
-              else if (k == 2) q2 = fmaf(d, d, q2); else q3 = fmaf(d, d, q3);
-            }
-          }
-          const float pq = (q0 + q1) + (q2 + q3);
-          mine_x[1] = pq;
-          *reinterpret_cast<float4*>(mine_x + 4) = make_float4(d0, d1, d2, d3);
-          pair_sync();
-          const float4 pd = *reinterpret_cast<const float4*>(peer_x + 4);
-          rstd = 1.0f / sqrtf(fmaf(pq + peer_x[1], 1.0f / PF_D, 1e-5f));
-          if (PROF) { if (rstd > -1.f) TOC(2, tp0); }
-          const float4 qi = *reinterpret_cast<const float4*>(mrow + 256);
-          qh[0] = phi_elu1(fmaf(rstd, d0 + pd.x, kc.bq[0])) * qi.x;
-          qh[1] = phi_elu1(fmaf(rstd, d1 + pd.y, kc.bq[1])) * qi.y;
-          qh[2] = phi_elu1(fmaf(rstd, d2 + pd.z, kc.bq[2])) * qi.z;
-          qh[3] = phi_elu1(fmaf(rstd, d3 + pd.w, kc.bq[3])) * qi.w;
-        }
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float4 m = *reinterpret_cast<const float4*>(mrow + 4 * (C0 + c));
-          float acc = kc.bo[C0 + c];
-          acc = fmaf(m.x, qh[0], acc); acc = fmaf(m.y, qh[1], acc); acc = fmaf(m.z, qh[2], acc); acc = fmaf(m.w, qh[3], acc);
-          xr[c] += acc;   // x2
-        }
-        // ---- LN_ffn statistics (exchange), independent of the slot waits ----
-        {
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-          for (int c = 0; c < 32; c += 4) { s0 += xr[c]; s1 += xr[c + 1]; s2 += xr[c + 2]; s3 += xr[c + 3]; }
-          const float ps = (s0 + s1) + (s2 + s3);
-          mine_x[2] = ps;
-          pair_sync();
-          mean = (ps + peer_x[2]) * (1.0f / PF_D);
-          float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-#pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            const float e0 = xr[c] - mean, e1 = xr[c + 1] - mean, e2 = xr[c + 2] - mean, e3 = xr[c + 3] - mean;
-            q0 = fmaf(e0, e0, q0); q1 = fmaf(e1, e1, q1); q2 = fmaf(e2, e2, q2); q3 = fmaf(e3, e3, q3);
-          }
-          const float pq = (q0 + q1) + (q2 + q3);
-          mine_x[3] = pq;
-          pair_sync();
-          rstd = 1.0f / sqrtf(fmaf(pq + peer_x[3], 1.0f / PF_D, 1e-5f));
-        }
-        // ---- wait for the slot, seed the GEMM2 accumulator with x2 + b2, write A1 ----
-        const int d = it % 3;
-        WAIT(0, BAR(2), par ^ 1);       // A1 free (both GEMM1 halves of the previous tile done)
-        WAIT(1, BAR(4 + d), (uint32_t)(((it / 3) & 1) ^ 1));   // D2[d] free (E2 of tile it-3 done)
-        tc_fence_after();
-#pragma unroll
-        for (int c4 = 0; c4 < 2; ++c4) {
-          uint32_t v[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(xr[16 * c4 + i] + kc.b2[C0 + 16 * c4 + i]);
-          tmem_st16(tmem + lane_base + WS_COL_D2 + 64 * d + C0 + 16 * c4, v);
-        }
-        {
-          unsigned char* a1hi = sm + WS_OFF_A1;
-          unsigned char* a1lo = a1hi + 16384;
-          const uint32_t rowoff = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
-          const u64 nm = pk2(-mean, -mean), rs = pk2(rstd, rstd);
-#pragma unroll
-          for (int cl = 0; cl < 4; ++cl) {  // 16-byte chunk = 8 channels
-            const int ch = 4 * HF + cl;
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const u64 nv = mul2(add2(pk2(xr[8 * cl + 2 * i], xr[8 * cl + 2 * i + 1]), nm), rs);
-              cvt2<FMT>(nv, hi[i], lo[i]);
-            }
-            const uint32_t off = rowoff + (uint32_t)(((ch ^ r) & 7) << 4);
-            *reinterpret_cast<uint4*>(a1hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            if (FMT == WS_FMT_BF16X3) *reinterpret_cast<uint4*>(a1lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          }
-        }
-        { const long long t0 = TIC(); tc_wait_st(); TOC(3, t0); }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        mbar_arrive(BAR(0));
-      }
-    };
-    if ((pw >> 2) == 0) body(std::integral_constant<int, 0>{});
-    else body(std::integral_constant<int, 1>{});
-  } else
-#else
   if (warp >= WS_PW0 && warp < WS_PW0 + WS_NPW) {
 #if WS_EW == 16
     asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");   // producer warpgroup takes the registers the MMA group returns
@@ -564,60 +379,11 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
       mbar_arrive(BAR(0));
     }
   } else
-#endif
   if (warp >= WS_MW) {
 #if WS_EW == 16
     asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");   // whole MMA warpgroup (issuer + 3 idle warps)
 #elif WS_EW == 12
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // 640 x 96 = 12x32x96 + 4x32x128 + 4x32x40 + slack
-#endif
-#if WS_STORE_WARPS
-    // ---- final-row store, one TMEM lane quadrant per warp of this warpgroup ----
-    const int sq = warp & 3;
-    const uint32_t s_lane_base = (uint32_t)(sq * 32) << 16;
-    const int sr = sq * 32 + lane, sg = sr >> 4, ss = sr & 15;
-    int sb_, sw_, spg_;
-    tm.decode((unsigned)t_begin, sb_, sw_, spg_);
-    int s_slot3 = 0;
-    uint32_t s_par3 = 0;
-    bool s_first = true;
-    auto store_tile = [&]() {   // D2[slot] (64 columns) of the next tile in order -> HBM
-      const int a = s_slot3;
-      WAIT(5, BAR(11 + a), s_par3);
-      tc_fence_after();
-      const int pair = spg_ * WS_G + sg, site = sw_ * WS_S + ss;
-      const bool valid = (pair < Pl) && (site < L);
-      float* dst = x + (((size_t)sb_ * Pl + (valid ? pair : 0)) * L + (valid ? site : 0)) * PF_D;
-      if (++spg_ == tm.nPG) { spg_ = 0; if (++sw_ == tm.nW) { sw_ = 0; ++sb_; } }
-      if (++s_slot3 == 3) { s_slot3 = 0; s_par3 ^= 1; }
-#pragma unroll
-      for (int jc = 0; jc < 4; jc += 2) {
-        uint32_t v0[16], v1[16];
-        tmem_ld16(tmem + s_lane_base + WS_COL_D2 + 64 * a + 16 * jc, v0);
-        tmem_ld16(tmem + s_lane_base + WS_COL_D2 + 64 * a + 16 * jc + 16, v1);
-        tc_wait_ld();
-        if (PROF && dump != nullptr && blockIdx.x == 0 && s_first) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            dump[sr * 320 + 256 + 16 * jc + i] = __uint_as_float(v0[i]);
-            dump[sr * 320 + 256 + 16 * jc + 16 + i] = __uint_as_float(v1[i]);
-          }
-        }
-        if (valid) {
-          stg256(dst + 16 * jc, v0);
-          stg256(dst + 16 * jc + 8, v0 + 8);
-          stg256(dst + 16 * jc + 16, v1);
-          stg256(dst + 16 * jc + 24, v1 + 8);
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(BAR(4 + a));
-      s_first = false;
-    };
-    if (warp != WS_MW) {
-#pragma unroll 1
-      for (int it = 0; it < n_my; ++it) store_tile();
-    }
 #endif
     if (warp == WS_MW) {
     // =============================== MMA ISSUER =============================================
@@ -689,9 +455,6 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
         }
         __syncwarp();
         TOC(3, t0);
-#if WS_STORE_WARPS
-        if (step >= 0 && half == 1) store_tile();   // tile `it`: its GEMM2 was just committed; nothing to issue meanwhile
-#endif
       }
     }
     }
@@ -796,13 +559,11 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
         e1(half, dump_this);
         mbar_arrive(BAR(9 + half));
       }
-#if !WS_STORE_WARPS
       if (half == 0 && step > 0) {   // after E1a(it): store tile it-1 (also the final tile at step == 2 n_my)
         const long long t0 = TIC();
         e2();
         TOC(5, t0);
       }
-#endif
     }
   }
   if (PROF && dump != nullptr && (tid == WS_PW0 * 32 || tid == WS_MW * 32 || tid == WS_EW0 * 32)) {
