@@ -157,8 +157,8 @@ __device__ __forceinline__ void store_tok(float* __restrict__ row, int j, const 
 __device__ __forceinline__ int chan_of(int j, int i) { return (i < 4) ? (4 * j + i) : (32 + 4 * j + (i - 4)); }
 
 // ---------------------------------------------------------------------------------------------
-// Packed-fp32 variants (FFMA2/FMUL2/FADD2, sm_100) used by the streaming kernels: the lane's 8
-// channels are held as 4 (even, odd) pairs in 64-bit registers.
+// Packed-fp32 helpers (FFMA2/FMUL2/FADD2, sm_100): two fp32 values in one 64-bit register.  Used by
+// the FFN kernel's GELU and LayerNorm statistics; the streaming kernels measured slower with them.
 // ---------------------------------------------------------------------------------------------
 typedef unsigned long long pf_u64;
 __device__ __forceinline__ pf_u64 pk2(float a, float b) { pf_u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
@@ -167,49 +167,6 @@ __device__ __forceinline__ pf_u64 fma2(pf_u64 a, pf_u64 b, pf_u64 c) { pf_u64 r;
 __device__ __forceinline__ pf_u64 mul2(pf_u64 a, pf_u64 b) { pf_u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ pf_u64 add2(pf_u64 a, pf_u64 b) { pf_u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ float hsum2(pf_u64 v) { float a, b; up2(v, a, b); return a + b; }
-
-// Token row access: two 128-bit accesses per lane (float4 chunk j and chunk 8+j), so that the 8
-// lanes of a slot cover one full 128-byte line per instruction; lane j therefore owns channels
-// 4j..4j+3 and 32+4j..32+4j+3 (chan_of), held as 4 (even, odd) pairs.
-__device__ __forceinline__ void load_tok8(const float* __restrict__ row, int j, pf_u64 (&x)[4]) {
-  const float4 a = reinterpret_cast<const float4*>(row)[j];
-  const float4 b = reinterpret_cast<const float4*>(row)[8 + j];
-  x[0] = pk2(a.x, a.y); x[1] = pk2(a.z, a.w); x[2] = pk2(b.x, b.y); x[3] = pk2(b.z, b.w);
-}
-__device__ __forceinline__ void store_tok8(float* __restrict__ row, int j, const pf_u64 (&x)[4]) {
-  float4 a, b;
-  up2(x[0], a.x, a.y); up2(x[1], a.z, a.w); up2(x[2], b.x, b.y); up2(x[3], b.z, b.w);
-  reinterpret_cast<float4*>(row)[j] = a;
-  reinterpret_cast<float4*>(row)[8 + j] = b;
-}
-// LayerNorm without affine on the packed layout (same definition as ln_normalize)
-__device__ __forceinline__ void ln_normalize2(const pf_u64 (&x)[4], pf_u64 (&n)[4]) {
-  float s = grp_sum(hsum2(add2(add2(x[0], x[1]), add2(x[2], x[3]))));
-  const float mean = s * (1.0f / PF_D);
-  const pf_u64 nm = pk2(-mean, -mean);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) n[i] = add2(x[i], nm);
-  pf_u64 q2 = mul2(n[0], n[0]);
-#pragma unroll
-  for (int i = 1; i < 4; ++i) q2 = fma2(n[i], n[i], q2);
-  const float q = grp_sum(hsum2(q2));
-  const float rstd = rsqrt_nr(fmaf(q, 1.0f / PF_D, 1e-5f));
-  const pf_u64 r2 = pk2(rstd, rstd);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) n[i] = mul2(n[i], r2);
-}
-// dot of this lane's 8 channels with a weight vector held as 4 pairs (partial: reduce over the group)
-__device__ __forceinline__ float dot8(const pf_u64 (&w)[4], const pf_u64 (&n)[4]) {
-  pf_u64 a = mul2(w[0], n[0]);
-#pragma unroll
-  for (int i = 1; i < 4; ++i) a = fma2(w[i], n[i], a);
-  return hsum2(a);
-}
-// this lane's 8 channels of a 64-vector (same mapping as load_tok8) as 4 pairs
-__device__ __forceinline__ void load8(const float* vec, int j, pf_u64 (&w)[4]) {
-  const float4 a = reinterpret_cast<const float4*>(vec)[j], b = reinterpret_cast<const float4*>(vec)[8 + j];
-  w[0] = pk2(a.x, a.y); w[1] = pk2(a.z, a.w); w[2] = pk2(b.x, b.y); w[3] = pk2(b.z, b.w);
-}
 
 // Lexicographic pair index -> (i, j), i < j < n   (model.py:13-17 order)
 __host__ __device__ inline void pair_to_ij(long long p, int n, int* pi, int* pj) {
