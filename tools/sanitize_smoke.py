@@ -11,11 +11,11 @@ m = Phyloformer(**ck["hyper_parameters"])
 m.load_state_dict({k.replace("model.", ""): v for k, v in ck["state_dict"].items() if k != "model.seq2pair"}, strict=False)
 m = m.cuda().eval()
 ref_w = pf_oracle.strip_prefix(ck["state_dict"])
-for shape in ((7, 37, 1), (5, 16, 2)):
+for shape in ((7, 37, 1), (5, 16, 2), (4, 9, 19)):   # the last one: 171 sites -> several finalize CTAs with a ragged tail
     n, L, B = shape
     idx = pf_oracle.synth_msa(n, L, seed=3, B=B)
     ref = pf_oracle.forward_idx(ref_w, idx).numpy()
-    for prec in ("fp32", "bf16x3", "bf16"):
+    for prec in ("fp32", "bf16x3", "fp16", "bf16"):
         m.set_precision(prec)
         d = m.forward_idx(idx.cuda(), squeeze=False)
         torch.cuda.synchronize()
