@@ -13,8 +13,8 @@
 //   warps 0..EW-1    EPILOGUE (EW = 8 or 16)  GELU on the GEMM1 accumulator in TMEM, rewritten in place as packed bf16
 //               hi/lo (FFMA2/FMUL2 packed-fp32 math); final rows TMEM -> HBM.
 //
-// A tile is 8 pairs x 16 consecutive sites (128 rows) so that the 16-site window of M_l
-// (16.6 KB) stays resident in shared memory while a CTA walks down the pairs; CTAs own
+// A tile is WS_G pairs x WS_S consecutive sites (128 rows; 32 x 4 by default) so that the WS_S-site
+// window of M_l stays resident in shared memory while a CTA walks down the pairs; CTAs own
 // contiguous tile ranges, window-major.  The hidden layer is processed in two 128-unit halves
 // with separate TMEM buffers and barriers, the A operand and the GEMM2 accumulator are double
 // buffered, so the tensor pipe, the producer and the epilogue run concurrently:
@@ -41,8 +41,13 @@
 #define WS_EW0 0                      // first epilogue warp
 #define WS_MW (WS_EW + WS_NPW)        // MMA warp (highest warp ids: highest issue priority)
 #define WS_THREADS ((WS_EW + WS_NPW + 4) * 32)
-#define WS_G 8    // pairs per tile
-#define WS_S 16   // sites per tile
+#ifndef WS_S_LOG2
+#define WS_S_LOG2 2                 // log2(sites per tile): 32 pairs x 4 sites.  Measured 16 / 8 / 4 / 2 / 1 sites:
+                                    // 32.9 / 32.7 / 32.1 / 31.9 / 32.5 ms (fewer distinct M_l rows per warp = fewer
+                                    // shared-memory wavefronts); 4 keeps 1 KB contiguous per pair and little tail waste
+#endif
+#define WS_S (1 << WS_S_LOG2)       // sites per tile
+#define WS_G (128 / WS_S)           // pairs per tile (128 token rows = the MMA's M)
 #define WS_OFF_A1 131072            // GEMM1 A operand: hi 16 KB + lo 16 KB (single buffer)
 #define WS_XROW 272                 // staged row stride: 256 B + 16 B pad (conflict-free LDS.128 per row)
 #define WS_OFF_XST 163840           // [128] rows prefetched with cp.async one tile ahead
@@ -238,7 +243,7 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
     // =============================== PRODUCER ===============================================
     const int ptid = tid - WS_PW0 * 32;  // 0..127
     const int r = ptid;                // row == TMEM lane
-    const int g = r >> 4, s = r & 15;
+    const int g = r >> WS_S_LOG2, s = r & (WS_S - 1);
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     int cur_b = -1, cur_w = -1;
     int b, w, pg;
@@ -462,7 +467,7 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
     // =============================== EPILOGUE ===============================================
     const int q = warp & 3, chf = (warp - WS_EW0) >> 2;   // TMEM lane quadrant, column group
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const int r = q * 32 + lane, g = r >> 4, s = r & 15;
+    const int r = q * 32 + lane, g = r >> WS_S_LOG2, s = r & (WS_S - 1);
     auto e1 = [&](int half, bool dump_this) {  // this warp's 16-column chunks of D1[half] -> gelu -> bf16 hi/lo in place
       // chunk j of the half (16 hidden units) belongs to column group j % WS_NCG
       constexpr int NCH = (8 - 1) / WS_NCG + 1;            // max chunks per warp and half
