@@ -197,3 +197,27 @@ def test_header_is_valid_c99_and_demo_compiles(tmp_path):
     subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
                     "-I", "/usr/local/cuda/include", "-c", os.path.join(ROOT, "tests", "cabi", "cabi_demo.c"),
                     "-o", str(tmp_path / "cabi_demo.o")], check=True)
+
+
+def test_host_entry_points_reject_bad_buffers():
+    """pf_parse_fasta / pf_format_phylip: size queries and undersized buffers are errors or size
+    reports, never overruns."""
+    import ctypes
+    import numpy as np
+    from phyloformer_b200 import _cabi
+    lib = _cabi.load()
+    text = b">a\nACDE\n>b\nACDE\n>c\nACDE\n"
+    codes = np.zeros(64, dtype=np.uint8)
+    off, ln = np.zeros(8, dtype=np.int64), np.zeros(8, dtype=np.int32)
+    L, bad = ctypes.c_int32(0), ctypes.c_int32(0)
+    args = lambda cap, mx: (text, len(text), codes.ctypes.data, cap, ctypes.byref(L), off.ctypes.data,   # noqa: E731
+                            ln.ctypes.data, mx, ctypes.byref(bad))
+    assert lib.pf_parse_fasta(*args(64, 8)) == 3 and L.value == 4
+    assert lib.pf_parse_fasta(*args(5, 8)) == -1            # PF_ERR_ARG: code buffer too small
+    assert b"too small" in lib.pf_last_error()
+    assert lib.pf_parse_fasta(*args(64, 2)) == -1           # more records than name slots
+    dm = np.zeros((2, 2), dtype=np.float32)
+    names = (ctypes.c_char_p * 2)(b"x", b"y")
+    need = lib.pf_format_phylip(dm.ctypes.data, 2, names, None, 0)      # size query
+    assert need == len("2\nx 0.0000000000 0.0000000000\ny 0.0000000000 0.0000000000\n")
+    assert lib.pf_format_phylip(dm.ctypes.data, 2, names, None, 10) < 0  # cap > 0 needs a buffer
