@@ -133,6 +133,13 @@ long long pf_parse_fasta(const char* text, long long len, uint8_t* codes, long l
 long long pf_format_phylip(const float* dm_host, int n, const char* const* names, char* out,
                            long long cap);
 
+/* Replaces skbio.tree.nj behind `infer_alns.py --trees` (infer_alns.py:120-123): host-only
+ * neighbour joining on the (n,n) fp32 matrix, Newick text (trifurcating root, "%.10f" branch
+ * lengths, negative lengths clipped to 0) into out[0..cap).  Same contract as pf_format_phylip:
+ * returns the text length, or a negative PF_ERR_*. */
+long long pf_neighbor_joining(const float* dm_host, int n, const char* const* names, char* out,
+                              long long cap);
+
 /* Kernel launches enqueued by the last pf_forward on this handle (for bench.py's
  * gpu_launches claim). */
 int pf_last_launch_count(pf_handle h);

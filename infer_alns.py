@@ -102,8 +102,8 @@ def main(argv=None):
             from skbio.tree import nj as sk_nj
             nj = lambda dm, ids: str(sk_nj(DistanceMatrix(dm, ids=ids)))  # noqa: E731
         except ImportError:
-            from phyloformer_b200.nj import neighbor_joining
-            nj = lambda dm, ids: neighbor_joining(dm, ids) + "\n"          # noqa: E731
+            from phyloformer_b200.nj import neighbor_joining_c
+            nj = lambda dm, ids: neighbor_joining_c(dm, ids) + "\n"        # noqa: E731
     if not torch.cuda.is_available():
         raise RuntimeError("infer_alns.py (B200 build) needs a CUDA device; there is no CPU fallback")
     if args.outdir is None:

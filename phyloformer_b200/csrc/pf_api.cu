@@ -611,6 +611,77 @@ long long pf_format_phylip(const float* dm_host, int n, const char* const* names
   return pos;   // bytes of text; the caller retries with a larger buffer if this exceeds cap
 }
 
+// ---- host-side neighbour joining (no device work) ---------------------------------------------
+// Saitou & Nei / Studier & Keppler, O(n^3) in double precision; same joins, tie-breaking (first
+// minimum of Q in row-major order) and Newick layout as phyloformer_b200/nj.py.
+long long pf_neighbor_joining(const float* dm_host, int n, const char* const* names, char* out, long long cap) {
+  if (!dm_host || !names || n < 1 || (cap > 0 && !out)) return (long long)fail(PF_ERR_ARG, "pf_neighbor_joining: bad argument");
+  for (int i = 0; i < n; ++i)
+    if (!names[i]) return (long long)fail(PF_ERR_ARG, "pf_neighbor_joining: null name %d", i);
+  auto fmt = [](double x) {
+    char b[400];
+    if (x < 0) x = 0.0;                      // clip negative branch lengths like nj.py
+    snprintf(b, sizeof(b), "%.10f", x);
+    return std::string(b);
+  };
+  std::string tree;
+  try {
+  if (n == 1) {
+    tree = std::string(names[0]) + ";";
+  } else if (n == 2) {
+    const double h = (double)dm_host[1] / 2;
+    tree = "(" + std::string(names[0]) + ":" + fmt(h) + "," + names[1] + ":" + fmt(h) + ");";
+  } else {
+    std::vector<double> d((size_t)n * n), r((size_t)n);
+    for (size_t i = 0; i < (size_t)n * n; ++i) d[i] = (double)dm_host[i];
+    std::vector<std::string> nodes((size_t)n);
+    std::vector<int> active((size_t)n);
+    for (int i = 0; i < n; ++i) { nodes[i] = names[i]; active[i] = i; }
+    auto D = [&](int i, int j) -> double& { return d[(size_t)i * n + j]; };
+    while (active.size() > 3) {
+      const int m = (int)active.size();
+      for (int a = 0; a < m; ++a) {
+        double s = 0.0;
+        for (int b = 0; b < m; ++b) s += D(active[a], active[b]);
+        r[a] = s;
+      }
+      double best = 0.0;
+      int ba = -1, bb = -1;
+      for (int a = 0; a < m; ++a)
+        for (int b = 0; b < m; ++b) {
+          if (a == b) continue;
+          const double q = (m - 2) * D(active[a], active[b]) - r[a] - r[b];
+          if (ba < 0 || q < best) { best = q; ba = a; bb = b; }
+        }
+      if (ba > bb) { const int t = ba; ba = bb; bb = t; }
+      const int ia = active[ba], ib = active[bb];
+      const double dab = D(ia, ib);
+      const double la = 0.5 * dab + (r[ba] - r[bb]) / (2.0 * (m - 2));
+      const double lb = dab - la;
+      nodes[ia] = "(" + nodes[ia] + ":" + fmt(la) + "," + nodes[ib] + ":" + fmt(lb) + ")";
+      nodes[ib].clear();
+      for (int k = 0; k < n; ++k) {            // the new node lives in ia's slot
+        const double dn = 0.5 * (D(ia, k) + D(ib, k) - dab);
+        D(ia, k) = dn;
+      }
+      for (int k = 0; k < n; ++k) D(k, ia) = D(ia, k);
+      D(ia, ia) = 0.0;
+      active.erase(active.begin() + bb);
+    }
+    const int i = active[0], j = active[1], k = active[2];
+    const double li = 0.5 * (D(i, j) + D(i, k) - D(j, k));
+    const double lj = 0.5 * (D(i, j) + D(j, k) - D(i, k));
+    const double lk = 0.5 * (D(i, k) + D(j, k) - D(i, j));
+    tree = "(" + nodes[i] + ":" + fmt(li) + "," + nodes[j] + ":" + fmt(lj) + "," + nodes[k] + ":" + fmt(lk) + ");";
+  }
+  } catch (...) {   // nothing may propagate across the C ABI
+    return (long long)fail(PF_ERR_ARG, "pf_neighbor_joining: out of host memory (n = %d)", n);
+  }
+  const long long len = (long long)tree.size();
+  if (len <= cap) memcpy(out, tree.data(), (size_t)len);
+  return len;
+}
+
 int pf_last_launch_count(pf_handle h) { return h ? h->launches : 0; }
 
 int pf_set_peer_exchange(pf_handle h, int rank, int world, void* const* peer_bufs_host, size_t slot_floats) {

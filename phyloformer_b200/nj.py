@@ -53,3 +53,25 @@ def neighbor_joining(dm: np.ndarray, ids: Sequence[str], clip_negative: bool = T
     lj = 0.5 * (d[i, j] + d[j, k] - d[i, k])
     lk = 0.5 * (d[i, k] + d[j, k] - d[i, j])
     return f"({nodes[i]}:{fmt(li)},{nodes[j]}:{fmt(lj)},{nodes[k]}:{fmt(lk)});"
+
+
+def neighbor_joining_c(dm: np.ndarray, ids: Sequence[str]) -> str:
+    """The same algorithm through the library's host-side pf_neighbor_joining (C, no GIL): what
+    the CLI uses.  `dm` is converted to fp32 (the model's output precision)."""
+    import ctypes
+    from . import _cabi
+    lib = _cabi.load()
+    n = len(ids)
+    d = np.ascontiguousarray(dm, dtype=np.float32)
+    if d.shape != (n, n):
+        raise ValueError("distance matrix and ids do not match")
+    names = (ctypes.c_char_p * n)(*[str(i).encode("utf8") for i in ids])
+    cap = 64 + sum(len(b) for b in names) + 40 * n
+    while True:
+        buf = ctypes.create_string_buffer(cap)
+        need = lib.pf_neighbor_joining(d.ctypes.data, n, names, buf, cap)
+        if need < 0:
+            raise _cabi.PfError(lib.pf_last_error().decode())
+        if need <= cap:
+            return buf.raw[:need].decode("utf8")
+        cap = need

@@ -36,3 +36,28 @@ def test_neighbor_joining_recovers_additive_trees():
         nwk = neighbor_joining(dm, names)
         assert rf_distance(nwk, trees[stem], min_length=1e-9) == 0, stem
     assert neighbor_joining(np.array([[0, 2.0], [2.0, 0]]), ["a", "b"]) == "(a:1.0000000000,b:1.0000000000);"
+
+
+def test_c_neighbor_joining_matches_python():
+    """pf_neighbor_joining (host-only C-ABI entry) against phyloformer_b200/nj.py: same topology and
+    branch lengths on additive and noisy matrices, same text in the degenerate cases."""
+    import re
+    import numpy as np
+    from phyloformer_b200.nj import neighbor_joining, neighbor_joining_c
+    from phyloformer_b200.treecmp import bipartitions, patristic_distances
+    rng = np.random.default_rng(5)
+    for n in (3, 4, 7, 20, 61):
+        x = rng.random((n, 5))
+        dm = np.abs(x[:, None, :] - x[None, :, :]).sum(-1) + rng.random((n, n)) * 0.01
+        dm = ((dm + dm.T) / 2).astype(np.float32)
+        np.fill_diagonal(dm, 0)
+        ids = [f"t{i}" for i in range(n)]
+        a, b = neighbor_joining(dm.astype(np.float64), ids), neighbor_joining_c(dm, ids)
+        assert bipartitions(a)[0] == bipartitions(b)[0]
+        la = [float(v) for v in re.findall(r":([0-9.]+)", a)]
+        lb = [float(v) for v in re.findall(r":([0-9.]+)", b)]
+        assert len(la) == len(lb) and np.allclose(la, lb, atol=2e-10)
+        (na, pa), (nb, pb) = patristic_distances(a), patristic_distances(b)
+        assert na == nb and np.abs(pa - pb).max() < 1e-8
+    assert neighbor_joining_c(np.array([[0, 2.0], [2.0, 0]]), ["a", "b"]) == "(a:1.0000000000,b:1.0000000000);"
+    assert neighbor_joining_c(np.zeros((1, 1)), ["solo"]) == "solo;"
