@@ -153,6 +153,9 @@ def cpu_oracle_rate(n, L, threads, repeats=1):
 
 def pick_cpu_sample(threads, budget_s):
     """Size a sample of the workload (fewer taxa/sites, same per-token work) to ~budget_s."""
+    if os.environ.get("PF_BENCH_CPU_SAMPLE"):               # "taxa x sites", e.g. 8x32 (tests)
+        n, L = (int(v) for v in os.environ["PF_BENCH_CPU_SAMPLE"].lower().split("x"))
+        return n, L
     rate, _ = cpu_oracle_rate(16, 128, threads)             # quick probe (~0.2 s)
     tokens = max(rate * budget_s, 2e4)
     for n, L in ((64, 500), (48, 400), (40, 250), (30, 200), (20, 200), (16, 128)):

@@ -221,3 +221,27 @@ def test_host_entry_points_reject_bad_buffers():
     need = lib.pf_format_phylip(dm.ctypes.data, 2, names, None, 0)      # size query
     assert need == len("2\nx 0.0000000000 0.0000000000\ny 0.0000000000 0.0000000000\n")
     assert lib.pf_format_phylip(dm.ctypes.data, 2, names, None, 10) < 0  # cap > 0 needs a buffer
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (CPU oracle port on the host cores) prints ONE JSON line with the
+    keys the driver reads; under torchrun only rank 0 prints.  Tiny sample so the test is quick."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, PF_BENCH_CPU_SAMPLE="8x32")
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "pair_sites_per_s" and d["steps"] == 2 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "sample" in d["config"]
+    r1 = subprocess.run(cmd, env=dict(env, RANK="1", WORLD_SIZE="2"), capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert r1.returncode == 0 and not [ln for ln in r1.stdout.splitlines() if ln.startswith("{")]
