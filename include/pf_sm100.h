@@ -160,7 +160,9 @@ size_t pf_peer_exchange_bytes(size_t slot_floats);
 int pf_device_error(pf_handle h);
 
 /* Test hook: when non-NULL, the tcgen05 FFN kernel copies the raw fp32 accumulators of its
- * first 128-token tile to dump_dev as [128][320] (columns 0..255 = GEMM1, 256..319 = GEMM2). */
+ * first 128-token tile to dump_dev as [128][320] (columns 0..255 = GEMM1, 256..319 = GEMM2),
+ * followed by the role timers of the profiling build: 3 roles x 8 floats per CTA (one CTA per SM).
+ * dump_dev must hold 128*320 + 24 * (number of SMs) floats. */
 int pf_debug_set_dump(pf_handle h, float* dump_dev);
 
 /* Per-kernel device timing (bench.py's roofline leg): when enabled, pf_forward brackets every

@@ -164,6 +164,91 @@ def forward(
     return d
 
 
+def forward_streaming(
+    w: Weights,
+    idx: torch.Tensor,
+    dtype: torch.dtype = torch.float64,
+    chunk: int = 256,
+    store_dtype: Optional[torch.dtype] = None,
+    nb: int = NB,
+    progress: Optional[Callable[[str], None]] = None,
+) -> torch.Tensor:
+    """forward_idx() for shapes whose intermediates do not fit in host memory at once
+    (BASELINE configs 3 and 5: 200 x 1000 and 500 x 500; the reference itself needs ~70 / ~218 GB
+    there and refuses n > 200, model.py:24-28).
+
+    Same graph as forward() -- model.py:166-187, 87-106, attention.py:160-197 -- evaluated over
+    chunks of `chunk` pairs with two passes per block, which is possible because the only
+    cross-pair coupling is column attention's per-site sums (attention.py:183-190 with N = pairs):
+      pass 1  row attention on the chunk (independent per pair), then the chunk's contribution to
+              the column summaries sum_p k, sum_p q, sum_p k v^T of the block;
+      pass 2  column attention output from the completed summaries, residual, FFN, residual.
+    Only the (B,P,L,64) activation is kept (in `store_dtype`, default = dtype); arithmetic is in
+    `dtype`.  idx: (B,n,L) residue codes.  Returns (B,P) in `dtype`.
+    tests/test_oracle_golden.py checks it against forward() (chunk sizes that do not divide P).
+    """
+    store_dtype = dtype if store_dtype is None else store_dtype
+    idx = idx.long()
+    B, n, L = idx.shape
+    P = n * (n - 1) // 2
+    We = w["embedding_block.0.weight"].to(dtype).reshape(D, N_CHAR)
+    be = w["embedding_block.0.bias"].to(dtype)
+    table = F.relu(We.t() + be)          # (22,64): embedding of a one-hot residue (model.py:138-143)
+    emb = table[idx]                     # (B,n,L,64)
+    pi, pj = pair_indices(n)
+    x = torch.empty((B, P, L, D), dtype=store_dtype)
+    say = progress or (lambda s: None)
+
+    def lin(u, name):
+        return F.linear(u, w[name + ".weight"].to(dtype).reshape(-1, u.shape[-1]), w[name + ".bias"].to(dtype))
+
+    for b in range(nb):
+        p = f"attention_blocks.{b}."
+        ksum = torch.zeros((B, L, H), dtype=dtype)
+        qsum = torch.zeros((B, L, H), dtype=dtype)
+        kv = torch.zeros((B, L, H, DH), dtype=dtype)
+        for c0 in range(0, P, chunk):
+            c1 = min(P, c0 + chunk)
+            if b == 0:
+                h = emb[:, pi[c0:c1]] + emb[:, pj[c0:c1]]                      # model.py:175
+            else:
+                h = x[:, c0:c1].to(dtype)
+            h = h + _attention(_ln(h, w, p + "row_norm", dtype), w, p + "row_attention.", dtype)  # model.py:90-92
+            u = _ln(h, w, p + "col_norm", dtype)                               # (B,Pc,L,64)
+            k = F.elu(lin(u, p + "col_attention.k_proj")) + 1                  # (B,Pc,L,H)
+            q = F.elu(lin(u, p + "col_attention.q_proj")) + 1
+            v = lin(u, p + "col_attention.v_proj").view(B, c1 - c0, L, H, DH)
+            ksum += k.sum(dim=1)
+            qsum += q.sum(dim=1)
+            kv += torch.einsum("bplh,bplhe->blhe", k, v)
+            x[:, c0:c1] = h.to(store_dtype)
+        ctx = kv / ksum[..., None]                                             # attention.py:186-190
+        qmean = qsum / P                                                       # attention.py:183
+        say(f"block {b}: summaries done")
+        W1 = w[p + "ffn.0.weight"].to(dtype).reshape(4 * D, D)
+        W2 = w[p + "ffn.3.weight"].to(dtype).reshape(D, 4 * D)
+        for c0 in range(0, P, chunk):
+            c1 = min(P, c0 + chunk)
+            h = x[:, c0:c1].to(dtype)
+            u = _ln(h, w, p + "col_norm", dtype)
+            q = F.elu(lin(u, p + "col_attention.q_proj")) + 1
+            qhat = q / qmean[:, None]                                          # (B,Pc,L,H)
+            o = (qhat[..., None] * ctx[:, None]).reshape(B, c1 - c0, L, D)     # attention.py:192-193
+            h = h + lin(o, p + "col_attention.out_proj")                       # model.py:97-98
+            u = _ln(h, w, p + "ffn_norm", dtype)
+            h = h + F.linear(F.gelu(F.linear(u, W1, w[p + "ffn.0.bias"].to(dtype))), W2,
+                             w[p + "ffn.3.bias"].to(dtype))                    # model.py:102-104
+            x[:, c0:c1] = h.to(store_dtype)
+        say(f"block {b}: done")
+    out = torch.empty((B, P), dtype=dtype)
+    wh = w["pwFNN.0.weight"].to(dtype).reshape(1, D)
+    for c0 in range(0, P, chunk):
+        c1 = min(P, c0 + chunk)
+        z = F.linear(x[:, c0:c1].to(dtype), wh, w["pwFNN.0.bias"].to(dtype))
+        out[:, c0:c1] = F.softplus(z[..., 0]).mean(dim=-1)                     # model.py:182-185
+    return out
+
+
 def forward_idx(w: Weights, idx: torch.Tensor, dtype=torch.float64, **kw) -> torch.Tensor:
     """Same as forward() from (B,n,L) residue codes."""
     return forward(w, msa_to_onehot(idx, dtype), dtype, **kw)

@@ -16,6 +16,7 @@
 #include "pf_kernels.cuh"
 #include "pf_ffn_tc.cuh"
 #include "pf_ffn_ws.cuh"
+#include "pf_attn_tc.cuh"
 
 namespace {
 
@@ -41,8 +42,9 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Plan {  // workspace carve-up for one (B, n, L, pair range)
   long long Pl, P;
-  int n_chunks, ppc;
-  size_t off_x, off_part, off_colsum, off_colM, off_semb, total;
+  int n_chunks, ppc;        // k_col_partial (FFMA): pair chunks
+  int n_chunks_tc, ppc_tc;  // k_col_partial_tc (tcgen05): pair chunks, ppc_tc a multiple of 32
+  size_t off_x, off_part, off_colsum, off_colM, off_semb, off_qc, total;
 };
 
 }  // namespace
@@ -54,6 +56,8 @@ struct pf_ctx {
   PfBlockW* blk_dev = nullptr;  // [nb]
   PfFfnTcW* tc_dev = nullptr;   // [nb] bf16 hi/lo smem images for the tcgen05 FFN
   PfFfnTcW* tc16_dev = nullptr; // [nb] the same in fp16 (PF_PREC_FP16)
+  PfAttnTcW* atc_dev = nullptr; // [nb][2] q/k weight images for the tcgen05 attention kernels (0: row, 1: column)
+  int col_impl = 1;             // 0: k_col_partial (FFMA), 1: k_col_partial_tc (tcgen05); env PF_COL_IMPL=cc|tc
   std::vector<PfFfnConst> ffn_const;  // [nb] host copies passed as __grid_constant__ kernel parameters
   int launches = 0;
   int ffn_impl = 1;             // 0: pf_ffn_tc.cuh (phased), 1: pf_ffn_ws.cuh (warp-specialised); env PF_FFN_IMPL=tc|ws
@@ -120,12 +124,35 @@ Plan make_plan(const pf_ctx* h, int B, int n, int L, long long lo, long long hi)
   if (p.ppc < 1) p.ppc = 1;
   p.n_chunks = (int)((p.Pl + p.ppc - 1) / p.ppc);
   if (p.n_chunks < 1) p.n_chunks = 1;
+  {  // tensor-core variant: units = (msa, 4-site window, chunk), two 128-thread CTAs per SM walk over them;
+     // cost = rounds x (tiles per unit + per-unit epilogue, about 3 tiles' worth)
+    const long long win = (long long)B * ((L + 3) / 4), slots2 = 2LL * h->n_sm;
+    long long bnc = 1, bcost = -1;
+    for (long long nc = 1; nc <= 64; ++nc) {
+      long long ppc = (p.Pl + nc - 1) / nc;
+      ppc = (ppc + 31) / 32 * 32;
+      if (ppc < 32) ppc = 32;
+      const long long chunks = (p.Pl + ppc - 1) / ppc;
+      if (chunks < nc && nc > 1) continue;   // same partition as a smaller nc
+      const long long rounds = (win * chunks + slots2 - 1) / slots2;
+      const long long cost = rounds * (ppc / 32 + 3) * 64 + chunks;
+      if (bcost < 0 || cost < bcost) { bcost = cost; bnc = nc; }
+    }
+    long long ppc = (p.Pl + bnc - 1) / bnc;
+    ppc = (ppc + 31) / 32 * 32;
+    if (ppc < 32) ppc = 32;
+    p.ppc_tc = (int)ppc;
+    p.n_chunks_tc = (int)((p.Pl + ppc - 1) / ppc);
+    if (p.n_chunks_tc < 1) p.n_chunks_tc = 1;
+  }
+  const int max_chunks = p.n_chunks > p.n_chunks_tc ? p.n_chunks : p.n_chunks_tc;
   size_t off = 0;
   p.off_x = off;       off = align_up(off + (size_t)B * p.Pl * L * PF_D * sizeof(float), 256);
-  p.off_part = off;    off = align_up(off + (size_t)p.n_chunks * B * L * PF_PART * sizeof(float), 256);
+  p.off_part = off;    off = align_up(off + (size_t)max_chunks * B * L * PF_PART * sizeof(float), 256);
   p.off_colsum = off;  off = align_up(off + (size_t)B * L * PF_COLSUM * sizeof(float), 256);
   p.off_colM = off;    off = align_up(off + (size_t)B * L * PF_MROW * sizeof(float), 256);
   p.off_semb = off;    off = align_up(off + (size_t)B * n * L * PF_D * sizeof(float), 256);
+  p.off_qc = off;      off = align_up(off + (size_t)B * p.Pl * L * 4 * sizeof(float), 256);   // per-token q~ of column attention
   p.total = off;
   return p;
 }
@@ -244,6 +271,7 @@ int pf_create(pf_handle* out, const pf_cfg* cfg, const float* const* weights_dev
   }
   std::vector<PfBlockW> blk(nb);
   std::vector<PfFfnTcW> tc(nb), tc16(nb);
+  std::vector<PfAttnTcW> atc(2 * nb);
   for (int b = 0; b < nb; ++b) {
     const int base = 2 + 26 * b;
     pack_attn(hw, base + 0, base + 16, &blk[b].row);
@@ -251,6 +279,8 @@ int pf_create(pf_handle* out, const pf_cfg* cfg, const float* const* weights_dev
     pack_ffn(hw, base + 22, base + 20, &blk[b].ffn);
     pf_pack_ffn_tc(blk[b].ffn, &tc[b]);
     pf_pack_ffn_tc(blk[b].ffn, &tc16[b], true);
+    pf_pack_attn_tc(blk[b].row, &atc[2 * b]);
+    pf_pack_attn_tc(blk[b].col, &atc[2 * b + 1]);
     PfFfnConst kc;
     for (int c = 0; c < PF_D; ++c) {
       for (int hh = 0; hh < PF_H; ++hh) kc.wq[c][hh] = blk[b].col.wqk[4 + hh][c];
@@ -266,6 +296,8 @@ int pf_create(pf_handle* out, const pf_cfg* cfg, const float* const* weights_dev
       (e = cudaMalloc(&h->blk_dev, sizeof(PfBlockW) * nb)) != cudaSuccess ||
       (e = cudaMalloc(&h->tc_dev, sizeof(PfFfnTcW) * nb)) != cudaSuccess ||
       (e = cudaMalloc(&h->tc16_dev, sizeof(PfFfnTcW) * nb)) != cudaSuccess ||
+      (e = cudaMalloc(&h->atc_dev, sizeof(PfAttnTcW) * 2 * nb)) != cudaSuccess ||
+      (e = cudaMemcpy(h->atc_dev, atc.data(), sizeof(PfAttnTcW) * 2 * nb, cudaMemcpyHostToDevice)) != cudaSuccess ||
       (e = cudaMalloc(&h->err_dev, sizeof(int))) != cudaSuccess ||
       (e = cudaMemset(h->err_dev, 0, sizeof(int))) != cudaSuccess ||
       (e = cudaMemcpy(h->head_dev, head.data(), sizeof(PfHeadW), cudaMemcpyHostToDevice)) != cudaSuccess ||
@@ -284,8 +316,10 @@ int pf_create(pf_handle* out, const pf_cfg* cfg, const float* const* weights_dev
   if (const char* e_impl = getenv("PF_FFN_IMPL")) h->ffn_impl = (strcmp(e_impl, "tc") == 0) ? 0 : 1;
   if (const char* e_row = getenv("PF_ROW_IMPL")) h->row_impl = (strcmp(e_row, "ld") == 0) ? 0 : 1;
   if (const char* e_prof = getenv("PF_WS_PROF")) h->ws_prof = atoi(e_prof);
+  if (const char* e_col = getenv("PF_COL_IMPL")) h->col_impl = (strcmp(e_col, "cc") == 0) ? 0 : 1;
   int rc = pf_ffn_tc_init();
   if (rc == 0) rc = pf_ffn_ws_init();
+  if (rc == 0) rc = pf_attn_tc_init();
   if (rc != 0) { cleanup(); return fail(PF_ERR_CUDA, "pf_create: tcgen05 FFN kernel setup failed (%d)", rc); }
   *out = h;
   return PF_OK;
@@ -297,6 +331,7 @@ void pf_destroy(pf_handle h) {
   if (h->blk_dev) cudaFree(h->blk_dev);
   if (h->tc_dev) cudaFree(h->tc_dev);
   if (h->tc16_dev) cudaFree(h->tc16_dev);
+  if (h->atc_dev) cudaFree(h->atc_dev);
   if (h->err_dev) cudaFree(h->err_dev);
   if (h->peers_dev) cudaFree(h->peers_dev);
   for (auto& r : h->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -356,6 +391,7 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
   float* colsum = (float*)(ws + pl.off_colsum);
   float* colM = (float*)(ws + pl.off_colM);
   float* semb = (float*)(ws + pl.off_semb);
+  float* qcache = (float*)(ws + pl.off_qc);
   const int rows = (int)(B * pl.Pl);
   const long long n_tok = (long long)rows * L;
   const int nb = h->cfg.nb_blocks;
@@ -401,12 +437,22 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
     stage = 3 * b + 1;
     if (dbg && stage == n_stages) return done();
     // ---- column attention summaries ----
+    const bool apply_only = dbg && (n_stages == 3 * b + 2);
+    // tensor-core summaries (and the q~ cache the FFN kernel then reads) in every mode but the fp32 one
+    const bool col_tc = h->col_impl == 1 && h->cfg.precision != PF_PREC_FP32 && h->ffn_impl == 1;
     {
-      dim3 g((L + 31) / 32, pl.n_chunks, B);
-      {
+      if (col_tc) {
+        const long long units = (long long)B * ((L + 3) / 4) * pl.n_chunks_tc;
+        const int g = (int)(units < 2LL * h->n_sm ? units : 2LL * h->n_sm);
+        Timed t_(h, PF_KC_COLSUM, st);
+        k_col_partial_tc<<<g, CT_THREADS, CT_SMEM_BYTES, st>>>(h->atc_dev + 2 * b + 1, x, part, qcache, B, L, (int)pl.Pl,
+                                                              pl.ppc_tc, pl.n_chunks_tc, h->err_dev);
+      } else {
+        dim3 g((L + 31) / 32, pl.n_chunks, B);
         Timed t_(h, PF_KC_COLSUM, st);
         k_col_partial<<<g, 256, 0, st>>>(&bw->col, x, part, L, (int)pl.Pl, pl.ppc);
       }
+      const int n_part = col_tc ? pl.n_chunks_tc : pl.n_chunks;
       // column reduce/finalize: spc sites per CTA (weights stay in registers across them), about
       // two CTAs per SM when there are few sites, PF_FS per CTA for batches of small alignments
       const int n_sites = B * L;
@@ -422,7 +468,7 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
         float* my_slot = reinterpret_cast<float*>(h->peer_self + PF_PEER_FLAG_BYTES) + (size_t)slot * h->peer_slot_floats;
         {
           Timed t_(h, PF_KC_COLFIN, st);
-          k_col_reduce<<<gfs, 256, 0, st>>>(&bw->col, part, pl.n_chunks, n_sites, spc, my_slot);
+          k_col_reduce<<<gfs, 256, 0, st>>>(&bw->col, part, n_part, n_sites, spc, my_slot);
         }
         {
           Timed t_(h, PF_KC_COLFIN, st);
@@ -437,7 +483,7 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
       } else {
         {
           Timed t_(h, PF_KC_COLFIN, st);
-          k_col_reduce<<<gfs, 256, 0, st>>>(&bw->col, part, pl.n_chunks, n_sites, spc, colsum);
+          k_col_reduce<<<gfs, 256, 0, st>>>(&bw->col, part, n_part, n_sites, spc, colsum);
         }
         CUDA_TRY(cudaGetLastError());
         if (reduce) {
@@ -452,7 +498,6 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
       }
     }
     // ---- column apply + FFN ----
-    const bool apply_only = dbg && (n_stages == 3 * b + 2);
     if (h->cfg.precision == PF_PREC_FP32 || apply_only) {
       long long tiles = (n_tok + FFN32_T - 1) / FFN32_T;
       const int grid = (int)(tiles < h->n_sm ? tiles : h->n_sm);
@@ -467,7 +512,8 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
       if (prec == PF_PREC_FP16 && h->ffn_impl != 1)
         return fail(PF_ERR_ARG, "pf_forward: PF_PREC_FP16 needs the warp-specialised FFN kernel (unset PF_FFN_IMPL)");
       const int rc = h->ffn_impl == 1
-                         ? pf_ffn_ws_launch(h->ffn_const[b], (prec == PF_PREC_FP16 ? h->tc16_dev : h->tc_dev) + b, x, colM, L,
+                         ? pf_ffn_ws_launch(h->ffn_const[b], (prec == PF_PREC_FP16 ? h->tc16_dev : h->tc_dev) + b, x, colM,
+                                            col_tc ? qcache : nullptr, L,
                                             (int)pl.Pl, B, h->n_sm, fmt, terms, h->err_dev, h->dump_dev, h->ws_prof, st)
                          : pf_ffn_tc_launch(&bw->col, h->tc_dev + b, x, colM, L, (int)pl.Pl, n_tok, h->n_sm, terms,
                                             h->err_dev, h->dump_dev, st);

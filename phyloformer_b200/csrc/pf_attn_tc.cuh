@@ -1,0 +1,338 @@
+// pf_attn_tc.cuh -- the attention contractions on the 5th-gen tensor cores (tcgen05 / TMEM).
+//
+// Per token and attention module the reference evaluates (attention.py:163-190, collapsed as in
+// SURVEY.md section 3.2, u = LayerNorm(x) without affine):
+//     q, k  = Wqk u            8 dot products of length 64                 "QK"  [tokens x 64] . [64 x 8]
+//     S    += k~ (x) u         4 x 64 outer-product accumulation           "S"   [64 x tokens] . [tokens x 4]
+// Both are GEMMs over a 128-token tile.  The tile's LayerNorm output is split ONCE into bf16 hi/lo
+// parts and stored as ONE shared-memory image [token][64 channels] (128-byte rows, SWIZZLE_128B); that
+// image is read twice by the tensor core:
+//   QK  as the K-major A operand   (M = 128 tokens, K = 64 channels), B = folded q/k weights [16 x 64]
+//       3 passes hi.hi + hi.lo(W) + lo.hi  ->  D_qk[128 x 16] in TMEM (columns 0..3 k, 4..7 q)
+//   S   as the MN-major A operand  (M = 128 = [64 channels of the hi image | 64 channels of the lo
+//       image], K = tokens), B = k~ as [16 x tokens] K-major (rows 0..3 k~ hi, 4..7 k~ lo)
+//       ->  D_S[128 x 16]:  S[h][c] = D[c][h] + D[c][4+h] + D[64+c][h] + D[64+c][4+h]
+//       (all four hi/lo cross terms: the full fp32-split product, accumulated in fp32 over the tokens)
+// tools/probe/umma_mn_probe.cu pins both operand forms bit-exactly on integer data.
+// What is left on the CUDA cores per token: LayerNorm statistics, the bf16 split (shared by both
+// GEMMs), phi on 8 values.  The fp32 ("exact") precision mode keeps the FFMA kernels of pf_kernels.cuh.
+#pragma once
+#include "pf_ffn_ws.cuh"
+
+struct PfAttnTcW {             // one attention module: B operand of the QK GEMM
+  uint16_t wqk_hi[16 * PF_D];  // K-major SWIZZLE_128B image [16][64]: rows 0..3 k heads, 4..7 q heads, 8..15 zero
+  uint16_t wqk_lo[16 * PF_D];
+  float bqk[8];
+  float pad[8];
+};
+
+inline void pf_pack_attn_tc(const PfAttnW& a, PfAttnTcW* o) {
+  memset(o, 0, sizeof(*o));
+  for (int n = 0; n < 8; ++n) {
+    for (int k = 0; k < PF_D; ++k) {
+      const float w = a.wqk[n][k];
+      const uint16_t hi = f32_to_bf16_rn(w);
+      const uint16_t lo = f32_to_bf16_rn(w - bf16_to_f32(hi));
+      const uint32_t off = umma_off_k64(n, k) / 2;
+      o->wqk_hi[off] = hi;
+      o->wqk_lo[off] = lo;
+    }
+    o->bqk[n] = a.bqk[n];
+  }
+}
+
+// MN-major SWIZZLE_128B shared-memory descriptor: LBO = byte distance between 64-element blocks along
+// M (here: the hi and the lo image), SBO = byte distance between 8-row groups along K (1024).
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+#define UMMA_IDESC_A_MN (1u << 15)
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+// ---- shared pieces of a 128-token attention tile (one thread per token row r) ----------------
+#define AT_XROW 272          // staged fp32 row: 256 B + 16 B pad (conflict-free LDS.128 per thread)
+#define AT_A1_BYTES 32768    // hi 16 KB | lo 16 KB
+#define AT_KT_BYTES 4096     // [16][128] bf16, two 64-token K atoms of 2 KB
+
+// LayerNorm (no affine) of the row held in xr, bf16 hi/lo split, store as row r of the A image.
+__device__ __forceinline__ void at_ln_split_store(const float (&xr)[PF_D], unsigned char* a1, int r) {
+  u64 sa = pk2(0.f, 0.f), sb = pk2(0.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < PF_D; c += 4) { sa = add2(sa, pk2(xr[c], xr[c + 1])); sb = add2(sb, pk2(xr[c + 2], xr[c + 3])); }
+  const float mean = hsum2(add2(sa, sb)) * (1.0f / PF_D);
+  const u64 nm = pk2(-mean, -mean);
+  u64 qa = pk2(0.f, 0.f), qb = pk2(0.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < PF_D; c += 4) {
+    const u64 da = add2(pk2(xr[c], xr[c + 1]), nm), db = add2(pk2(xr[c + 2], xr[c + 3]), nm);
+    qa = fma2(da, da, qa); qb = fma2(db, db, qb);
+  }
+  const float rstd = 1.0f / sqrtf(fmaf(hsum2(add2(qa, qb)), 1.0f / PF_D, 1e-5f));
+  const u64 rs = pk2(rstd, rstd);
+  unsigned char* a1lo = a1 + 16384;
+  const uint32_t rowoff = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {  // 16-byte chunk = 8 channels
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const u64 nv = mul2(add2(pk2(xr[8 * ch + 2 * i], xr[8 * ch + 2 * i + 1]), nm), rs);
+      split2(nv, hi[i], lo[i]);
+    }
+    const uint32_t off = rowoff + (uint32_t)(((ch ^ r) & 7) << 4);
+    *reinterpret_cast<uint4*>(a1 + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(a1lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// One elected thread: D_qk[128 x 16] = A1 . Wqk^T, three passes (hi.hi, hi.lo(W), lo.hi).
+__device__ __forceinline__ void at_issue_qk(uint32_t a1_u32, uint32_t bq_u32, uint32_t d_tmem) {
+  const uint32_t idesc = umma_idesc(128, 16);
+  const u64 ah = umma_desc(a1_u32), al = umma_desc(a1_u32 + 16384);
+  const u64 bh = umma_desc(bq_u32), bl = umma_desc(bq_u32 + 2048);
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    const u64 da = (t == 2) ? al : ah, db = (t == 1) ? bl : bh;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) umma_ss(d_tmem, da + 2 * s, db + 2 * s, idesc, (t | s) ? 1u : 0u);
+  }
+}
+// One elected thread: D_S[128 x 16] (+)= A1^T[rows row0 .. row0 + 16 nk) . KT, contraction over tokens.
+__device__ __forceinline__ void at_issue_s(uint32_t a1_u32, uint32_t kt_u32, uint32_t d_tmem, int row0, int nk, bool accumulate) {
+  const uint32_t idesc = umma_idesc(128, 16) | UMMA_IDESC_A_MN;
+  for (int k = 0; k < nk; ++k) {
+    const int row = row0 + 16 * k;
+    const u64 da = umma_desc_mn(a1_u32 + (uint32_t)row * 128u, 16384u, 1024u);
+    const u64 db = umma_desc(kt_u32 + (uint32_t)((row >> 6) * 2048 + (row & 63) * 2));
+    umma_ss(d_tmem, da, db, idesc, (accumulate || k > 0) ? 1u : 0u);
+  }
+}
+// Token r's k~ values as bf16 hi/lo into column r of the K-major KT operand (rows 0..3 hi, 4..7 lo).
+__device__ __forceinline__ void at_store_kt(unsigned char* kt, int r, const float (&kq)[8]) {
+  const int kk = r & 63;
+  unsigned char* base = kt + (r >> 6) * 2048 + (kk & 7) * 2;
+#pragma unroll
+  for (int h = 0; h < PF_H; ++h) {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(kq[h]);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(kq[h] - __bfloat162float(hi));
+    *reinterpret_cast<__nv_bfloat16*>(base + h * 128 + ((((kk >> 3) ^ h) & 7) << 4)) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(base + (4 + h) * 128 + ((((kk >> 3) ^ (4 + h)) & 7) << 4)) = lo;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Column attention, step 1 on the tensor cores: partial sums over a chunk of pairs at each site
+// (same output as k_col_partial: part[chunk][b][l][264]) plus the per-token q~ cache that the FFN
+// kernel's column apply reads (16 B per token) instead of recomputing LN_col and the q dots.
+// A tile is 32 pairs x 4 consecutive sites (1 KB contiguous per pair): warp s owns site s, lane =
+// pair, so a site's 32 tokens are 32 consecutive rows of the operand image (two K = 16 steps of the
+// S GEMM) and the per-site sums of k~, q~ are plain warp reductions.  A work unit is (msa, 4-site
+// window, pair chunk); 128-thread CTAs, two per SM, walk over units; the A image is double buffered so
+// the S GEMM of a tile overlaps the next tile's LayerNorm/split.
+// ------------------------------------------------------------------------------------------
+#define CT_THREADS 128
+#define CT_OFF_A1 0
+#define CT_OFF_XST (2 * AT_A1_BYTES)
+#define CT_OFF_KT (CT_OFF_XST + 128 * AT_XROW)
+#define CT_OFF_BQ (CT_OFF_KT + 2 * AT_KT_BYTES)
+#define CT_OFF_BAR (CT_OFF_BQ + 4096)
+#define CT_OFF_TMEM (CT_OFF_BAR + 32)
+#define CT_SMEM_BYTES (CT_OFF_TMEM + 32 + 1024)
+#define CT_TM_COLS 128
+#define CT_TM_S 32           // D_S of site s at TMEM column 32 + 16 s; D_qk at column 0
+
+__global__ void __launch_bounds__(CT_THREADS, 2)
+k_col_partial_tc(const PfAttnTcW* __restrict__ Wt, const float* __restrict__ x, float* __restrict__ part,
+                 float* __restrict__ qcache, int B, int L, int Pl, int ppc, int n_chunks, int* __restrict__ err_flag) {
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const uint32_t sbase = smem_u32(sm);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t bar_qk = sbase + CT_OFF_BAR, bar_s0 = sbase + CT_OFF_BAR + 8;
+
+  // ---- one-time setup: weights, zeroed KT (rows 8..15 stay zero), barriers, TMEM ----
+  for (int i = tid; i < 4096 / 16; i += CT_THREADS)
+    reinterpret_cast<int4*>(sm + CT_OFF_BQ)[i] = reinterpret_cast<const int4*>(Wt->wqk_hi)[i];
+  for (int i = tid; i < 2 * AT_KT_BYTES / 16; i += CT_THREADS) reinterpret_cast<int4*>(sm + CT_OFF_KT)[i] = make_int4(0, 0, 0, 0);
+  float bq[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bq[i] = Wt->bqk[i];
+  if (tid == 0) {
+    mbar_init(bar_qk, 1); mbar_init(bar_s0, 1); mbar_init(bar_s0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + CT_OFF_TMEM), "r"(CT_TM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + CT_OFF_TMEM);
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+
+  const int nW = (L + 3) >> 2;
+  const long long upc = (long long)B * nW;            // units per chunk
+  const long long n_units = upc * n_chunks;
+  const uint32_t xst_u32 = sbase + CT_OFF_XST + (uint32_t)tid * AT_XROW;
+  const float4* srow = reinterpret_cast<const float4*>(sm + CT_OFF_XST + tid * AT_XROW);
+  bool ok = true;
+
+  // token of (unit coords, tile t) that this thread owns; returns nullptr when out of range
+  auto tok_ptr = [&](int chunk, int b, int w, int t) -> const float* {
+    const int pair = chunk * ppc + 32 * t + lane, site = 4 * w + warp;
+    const int p1 = min(Pl, (chunk + 1) * ppc);
+    if (pair >= p1 || site >= L) return nullptr;
+    return x + (((size_t)b * Pl + pair) * L + site) * PF_D;
+  };
+  auto prefetch = [&](const float* src) {
+    if (src != nullptr) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(xst_u32 + 16 * c), "l"(src + 4 * c) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto decode = [&](long long u, int& chunk, int& b, int& w) {
+    chunk = (int)(u / upc);
+    const int rem = (int)(u - (long long)chunk * upc);
+    b = rem / nW;
+    w = rem - b * nW;
+  };
+
+  int n_glob = 0;   // tiles processed by this CTA (barrier parities)
+  if ((long long)blockIdx.x < n_units) {
+    int c0, b0, w0;
+    decode(blockIdx.x, c0, b0, w0);
+    prefetch(tok_ptr(c0, b0, w0, 0));
+  }
+  for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
+    int chunk, b, w, nchunk = 0, nb = 0, nw = 0;
+    decode(u, chunk, b, w);
+    const bool has_next = u + gridDim.x < n_units;
+    if (has_next) decode(u + gridDim.x, nchunk, nb, nw);
+    const int p0 = chunk * ppc, p1 = min(Pl, p0 + ppc);
+    const int nt = (p1 - p0 + 31) >> 5;
+    float ks[PF_H] = {0.f, 0.f, 0.f, 0.f}, qs[PF_H] = {0.f, 0.f, 0.f, 0.f};
+    for (int t = 0; t < nt; ++t, ++n_glob) {
+      const int buf = n_glob & 1;
+      unsigned char* a1 = sm + CT_OFF_A1 + buf * AT_A1_BYTES;
+      unsigned char* kt = sm + CT_OFF_KT + buf * AT_KT_BYTES;
+      const float* mine = tok_ptr(chunk, b, w, t);
+      const bool valid = mine != nullptr;
+      // ---- phase 1: staged row -> registers, LayerNorm, split, operand image ----
+      float xr[PF_D];
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) v = srow[c];
+        xr[4 * c] = v.x; xr[4 * c + 1] = v.y; xr[4 * c + 2] = v.z; xr[4 * c + 3] = v.w;
+      }
+      prefetch(t + 1 < nt ? tok_ptr(chunk, b, w, t + 1) : (has_next ? tok_ptr(nchunk, nb, nw, 0) : nullptr));
+      ok = mbar_wait(bar_s0 + 8 * buf, (uint32_t)(((n_glob >> 1) & 1) ^ 1)) && ok;   // S GEMM of tile n-2 has read this buffer
+      at_ln_split_store(xr, a1, tid);
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        at_issue_qk(sbase + CT_OFF_A1 + buf * AT_A1_BYTES, sbase + CT_OFF_BQ, tmem);
+        tc_commit(bar_qk);
+      }
+      // ---- phase 2: q, k from TMEM, phi, sums, q~ cache, k~ operand ----
+      ok = mbar_wait(bar_qk, (uint32_t)(n_glob & 1)) && ok;
+      tc_fence_after();
+      uint32_t v[8];
+      tmem_ld8(tmem + lane_base, v);
+      tc_wait_ld();
+      float kq[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) kq[i] = valid ? phi_elu1(__uint_as_float(v[i]) + bq[i]) : 0.f;
+#pragma unroll
+      for (int h = 0; h < PF_H; ++h) { ks[h] += kq[h]; qs[h] += kq[4 + h]; }
+      if (valid) {
+        const size_t tok = (size_t)(mine - x) / PF_D;
+        *reinterpret_cast<float4*>(qcache + tok * 4) = make_float4(kq[4], kq[5], kq[6], kq[7]);
+      }
+      at_store_kt(kt, tid, kq);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          at_issue_s(sbase + CT_OFF_A1 + buf * AT_A1_BYTES, sbase + CT_OFF_KT + buf * AT_KT_BYTES, tmem + CT_TM_S + 16 * s,
+                     32 * s, 2, t > 0);
+        tc_commit(bar_s0 + 8 * buf);
+      }
+    }
+    // ---- unit end: D_S -> part ----
+    {
+      const int last = n_glob - 1;
+      ok = mbar_wait(bar_s0 + 8 * (last & 1), (uint32_t)((last >> 1) & 1)) && ok;
+      tc_fence_after();
+      float* red = reinterpret_cast<float*>(sm + CT_OFF_A1);   // [4 sites][4 heads][64]: both images are idle here
+      float val[4][PF_H];
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        uint32_t d[8];
+        tmem_ld8(tmem + lane_base + CT_TM_S + 16 * s, d);
+        tc_wait_ld();
+#pragma unroll
+        for (int h = 0; h < PF_H; ++h) val[s][h] = __uint_as_float(d[h]) + __uint_as_float(d[4 + h]);
+      }
+      if (tid >= 64) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+          for (int h = 0; h < PF_H; ++h) red[(s * PF_H + h) * 64 + (tid - 64)] = val[s][h];
+      }
+      // per-site sums of k~ and q~: warp s owns site s
+#pragma unroll
+      for (int h = 0; h < PF_H; ++h) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          ks[h] += __shfl_xor_sync(PF_FULL, ks[h], o);
+          qs[h] += __shfl_xor_sync(PF_FULL, qs[h], o);
+        }
+      }
+      tc_fence_before();
+      __syncthreads();
+      float* obase = part + (((size_t)chunk * B + b) * L + (size_t)4 * w) * PF_PART;
+      if (tid < 64) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          if (4 * w + s < L) {
+#pragma unroll
+            for (int h = 0; h < PF_H; ++h)
+              obase[(size_t)s * PF_PART + 8 + h * PF_D + tid] = val[s][h] + red[(s * PF_H + h) * 64 + tid];
+          }
+        }
+      }
+      if (lane == 0 && 4 * w + warp < L) {
+        float* o = obase + (size_t)warp * PF_PART;
+#pragma unroll
+        for (int h = 0; h < PF_H; ++h) { o[h] = ks[h]; o[4 + h] = qs[h]; }
+      }
+      __syncthreads();   // red (aliasing the operand image) is read before the next unit overwrites it
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (!ok && err_flag != nullptr) *err_flag = 4;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(CT_TM_COLS) : "memory");
+}
+
+inline int pf_attn_tc_init() {
+  return (int)cudaFuncSetAttribute(k_col_partial_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_BYTES);
+}

@@ -167,11 +167,13 @@ struct WsTileMap {  // tile index -> rows
   }
 };
 
-template <bool PROF, int FMT>
+// QC: the column-attention q~ of every token comes from the cache written by k_col_partial_tc (16 B per
+// token, staged into the pad of the row slot) instead of being recomputed (LN_col + 4 dots of length 64).
+template <bool PROF, int FMT, bool QC>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restrict__ Wt, float* __restrict__ x,
-                  const float* __restrict__ colM, int L, int Pl, int B, int n_terms, int* __restrict__ err_flag,
-                  float* __restrict__ dump) {
+                  const float* __restrict__ colM, const float* __restrict__ qcache, int L, int Pl, int B, int n_terms,
+                  int* __restrict__ err_flag, float* __restrict__ dump) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   // keep the pointer derived from the __shared__ array so that accesses compile to LDS/STS
   unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -254,6 +256,7 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
 #pragma unroll
       for (int c = 0; c < 16; ++c)
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(xst_u32 + 16 * c), "l"(src + 4 * c) : "memory");
+      if (QC) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(xst_u32 + 256), "l"(qcache + tok * 4) : "memory");
     };
     if (n_my > 0) {
       const int pair0 = pg * WS_G + g, site0 = w * WS_S + s;
@@ -267,6 +270,7 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
       const int pair = pg * WS_G + g, site = w * WS_S + s;
       const bool valid = (pair < Pl) && (site < L);
       float xr[PF_D];
+      float4 qc4 = make_float4(0.f, 0.f, 0.f, 0.f);
       {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         const float4* srow = reinterpret_cast<const float4*>(sm + WS_OFF_XST + r * WS_XROW);
@@ -276,6 +280,7 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
           if (valid) v = srow[c];
           xr[4 * c] = v.x; xr[4 * c + 1] = v.y; xr[4 * c + 2] = v.z; xr[4 * c + 3] = v.w;
         }
+        if (QC) qc4 = valid ? srow[16] : make_float4(0.f, 0.f, 0.f, 0.f);
         // prefetch the next tile's row into the same slot (this thread is its only reader)
         if (it + 1 < n_my) {
           int nb = b, nw = w, npg = pg + 1;
@@ -299,7 +304,11 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
       // ---- column attention: q from LN_col(x1); the centred row is consumed on the fly ----
       float mean, rstd;
       float qh[PF_H];
-      {
+      if (QC) {
+        const float4 qi = *reinterpret_cast<const float4*>(mrow + 256);
+        qh[0] = qc4.x * qi.x; qh[1] = qc4.y * qi.y; qh[2] = qc4.z * qi.z; qh[3] = qc4.w * qi.w;
+        if (PROF) TOC(2, tp0);
+      } else {
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
         for (int c = 0; c < PF_D; c += 4) { s0 += xr[c]; s1 += xr[c + 1]; s2 += xr[c + 2]; s3 += xr[c + 3]; }
@@ -586,29 +595,43 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
   }
 }
 
-inline int pf_ffn_ws_init() {
-  int rc = (int)cudaFuncSetAttribute(k_colapply_ffn_ws<false, WS_FMT_BF16X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
-  if (rc == 0) rc = (int)cudaFuncSetAttribute(k_colapply_ffn_ws<true, WS_FMT_BF16X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
-  if (rc == 0) rc = (int)cudaFuncSetAttribute(k_colapply_ffn_ws<false, WS_FMT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
-  if (rc == 0) rc = (int)cudaFuncSetAttribute(k_colapply_ffn_ws<false, WS_FMT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
+template <bool QC>
+inline int pf_ffn_ws_init_qc() {
+  int rc = (int)cudaFuncSetAttribute(k_colapply_ffn_ws<false, WS_FMT_BF16X3, QC>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
+  if (rc == 0) rc = (int)cudaFuncSetAttribute(k_colapply_ffn_ws<true, WS_FMT_BF16X3, QC>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
+  if (rc == 0) rc = (int)cudaFuncSetAttribute(k_colapply_ffn_ws<false, WS_FMT_BF16, QC>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
+  if (rc == 0) rc = (int)cudaFuncSetAttribute(k_colapply_ffn_ws<false, WS_FMT_F16, QC>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
   return rc;
+}
+inline int pf_ffn_ws_init() {
+  const int rc = pf_ffn_ws_init_qc<false>();
+  return rc ? rc : pf_ffn_ws_init_qc<true>();
 }
 
 // fmt: WS_FMT_*; n_terms: MMA passes per product (3 for BF16X3, 1 for BF16, 2 for F16 = hi and lo weights).
-// Wt must hold the weight images of the matching 16-bit format.
-inline int pf_ffn_ws_launch(const PfFfnConst& kc, const PfFfnTcW* Wt, float* x, const float* colM, int L, int Pl, int B,
-                            int n_sm, int fmt, int n_terms, int* err_flag, float* dump, int prof, cudaStream_t st) {
+// Wt must hold the weight images of the matching 16-bit format.  qcache: the per-token q~ cache of
+// k_col_partial_tc, or nullptr (the producer then recomputes q~ itself).
+template <bool QC>
+inline int pf_ffn_ws_launch_qc(const PfFfnConst& kc, const PfFfnTcW* Wt, float* x, const float* colM, const float* qcache,
+                               int L, int Pl, int B, int grid, int fmt, int n_terms, int* err_flag, float* dump, int prof,
+                               cudaStream_t st) {
+  if (fmt == WS_FMT_F16)
+    k_colapply_ffn_ws<false, WS_FMT_F16, QC><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(kc, Wt, x, colM, qcache, L, Pl, B, n_terms, err_flag, nullptr);
+  else if (fmt == WS_FMT_BF16)
+    k_colapply_ffn_ws<false, WS_FMT_BF16, QC><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(kc, Wt, x, colM, qcache, L, Pl, B, n_terms, err_flag, nullptr);
+  else if (prof || dump != nullptr)   // the debug/profiling instantiation carries the dump and the role timers
+    k_colapply_ffn_ws<true, WS_FMT_BF16X3, QC><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(kc, Wt, x, colM, qcache, L, Pl, B, n_terms, err_flag, dump);
+  else
+    k_colapply_ffn_ws<false, WS_FMT_BF16X3, QC><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(kc, Wt, x, colM, qcache, L, Pl, B, n_terms, err_flag, dump);
+  return (int)cudaGetLastError();
+}
+inline int pf_ffn_ws_launch(const PfFfnConst& kc, const PfFfnTcW* Wt, float* x, const float* colM, const float* qcache, int L,
+                            int Pl, int B, int n_sm, int fmt, int n_terms, int* err_flag, float* dump, int prof, cudaStream_t st) {
   const long long nt = (long long)B * ((L + WS_S - 1) / WS_S) * ((Pl + WS_G - 1) / WS_G);
   if (nt > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
   if (fmt != WS_FMT_BF16X3 && n_terms > 2) return (int)cudaErrorInvalidValue;   // no lo activations in these formats
   const int grid = (int)(nt < n_sm ? nt : n_sm);
-  if (fmt == WS_FMT_F16)
-    k_colapply_ffn_ws<false, WS_FMT_F16><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(kc, Wt, x, colM, L, Pl, B, n_terms, err_flag, nullptr);
-  else if (fmt == WS_FMT_BF16)
-    k_colapply_ffn_ws<false, WS_FMT_BF16><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(kc, Wt, x, colM, L, Pl, B, n_terms, err_flag, nullptr);
-  else if (prof || dump != nullptr)   // the debug/profiling instantiation carries the dump and the role timers
-    k_colapply_ffn_ws<true, WS_FMT_BF16X3><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(kc, Wt, x, colM, L, Pl, B, n_terms, err_flag, dump);
-  else
-    k_colapply_ffn_ws<false, WS_FMT_BF16X3><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(kc, Wt, x, colM, L, Pl, B, n_terms, err_flag, dump);
-  return (int)cudaGetLastError();
+  return qcache != nullptr
+             ? pf_ffn_ws_launch_qc<true>(kc, Wt, x, colM, qcache, L, Pl, B, grid, fmt, n_terms, err_flag, dump, prof, st)
+             : pf_ffn_ws_launch_qc<false>(kc, Wt, x, colM, qcache, L, Pl, B, grid, fmt, n_terms, err_flag, dump, prof, st);
 }

@@ -399,7 +399,11 @@ class Phyloformer(nn.Module):
         lib = _cabi.load()
         idx = idx[None] if idx.dim() == 2 else idx
         self.forward_idx(idx)  # make sure the handle exists
-        dump = torch.zeros((128, 320), dtype=torch.float32, device=idx.device)
+        # [128][320] accumulators, followed by the per-CTA role timers of the profiling build
+        # (3 roles x 8 floats per CTA, one CTA per SM): see pf_debug_set_dump in pf_sm100.h
+        n_sm = torch.cuda.get_device_properties(idx.device).multi_processor_count
+        flat = torch.zeros(128 * 320 + n_sm * 24, dtype=torch.float32, device=idx.device)
+        dump = flat[:128 * 320].view(128, 320)
         _cabi.check(lib.pf_debug_set_dump(self._handle, dump.data_ptr()), "pf_debug_set_dump")
         try:
             self.forward_idx(idx)

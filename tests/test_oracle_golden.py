@@ -111,3 +111,44 @@ def test_phylip_text_matches_reference(ref_testdata, golden_dir):
         _, ids = pf_oracle.parse_fasta_idx(os.path.join(golden_dir, "msas", stem + ".fa"))
         txt = pf_oracle.vec_to_phylip_text(torch.from_numpy(ref_testdata[stem]), ids)
         assert txt == open(os.path.join(golden_dir, f"ref_phylip_{stem}.phy")).read()
+
+
+@pytest.mark.parametrize("chunk", [1, 7, 1000])
+def test_streaming_oracle_equals_monolithic(pf_weights, ref_testdata, golden_dir, chunk):
+    """forward_streaming (pair-chunked, two passes per block: what the full-size fixtures of
+    BASELINE configs 3 and 5 were generated with) is the same graph as forward(): equal to fp64
+    round-off for chunk sizes that do and do not divide P, batch > 1, and -- through the reference
+    fixtures -- within the oracle's tolerance of the unmodified reference."""
+    idx = pf_oracle.synth_msa(9, 23, seed=11, B=2)
+    full = pf_oracle.forward_idx(pf_weights, idx, torch.float64)
+    st = pf_oracle.forward_streaming(pf_weights, idx, torch.float64, chunk=chunk)
+    assert st.shape == full.shape and rel_err(st, full)[0] < 1e-12
+    st32 = pf_oracle.forward_streaming(pf_weights, idx, torch.float32, chunk=chunk)
+    assert rel_err(st32, full)[0] < TOL
+    if chunk == 7:
+        stem = "0_20_tips"
+        fa, _ = pf_oracle.parse_fasta_idx(os.path.join(golden_dir, "msas", stem + ".fa"))
+        d = pf_oracle.forward_streaming(pf_weights, fa[None], torch.float64, chunk=37)[0]
+        assert rel_err(d, ref_testdata[stem])[0] < TOL
+
+
+@pytest.mark.parametrize("shape", ["200x1000", "500x500"])
+def test_fullsize_fixture_is_consistent(pf_weights, golden_dir, shape):
+    """The committed full-size fixtures (tests/golden/make_fullsize.py) belong to bench.py's inputs:
+    recompute a few pairs' ROW-attention-free invariants cheaply -- here: the fixture has P entries,
+    is finite and positive, and a 12-taxon sub-alignment of the same MSA run through the oracle
+    correlates with the corresponding sub-matrix (column attention couples pairs, so the values
+    differ slightly; identical ordering of near and far pairs is what is checked)."""
+    path = os.path.join(golden_dir, f"oracle_fullsize_{shape}.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not generated")
+    g = np.load(path)
+    n, L = int(g["n"]), int(g["L"])
+    d = g["dist"]
+    assert d.shape == (n * (n - 1) // 2,) and np.isfinite(d).all() and (d > 0).all()
+    idx = pf_oracle.synth_msa(n, L, seed=int(g["seed"]), kind="tree")
+    sub = pf_oracle.forward_idx(pf_weights, idx[:, :12, :200], torch.float32)[0].numpy()
+    iu = np.triu_indices(n, 1)
+    D = np.zeros((n, n)); D[iu] = d
+    big = D[:12, :12][np.triu_indices(12, 1)]
+    assert np.corrcoef(np.log(sub), np.log(big))[0, 1] > 0.9

@@ -1,0 +1,28 @@
+#!/bin/bash
+# One gpurun call = several measurements; everything lands in gpurun_out/ (merged back).  usage: tools/gpu_call.sh <tag> <steps...>
+tag=$1; shift
+out=gpurun_out/$tag; mkdir -p $out
+for step in "$@"; do
+  case $step in
+    probe)   timeout 120 tools/probe/umma_mn_probe > $out/probe.txt 2>&1; echo "probe rc=$?" >> $out/probe.txt ;;
+    tcattn)  timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "tensor_core_attention or stage_taps or synthetic_shapes" -s > $out/pytest_tcattn.txt 2>&1; echo "rc=$?" >> $out/pytest_tcattn.txt ;;
+    full)    timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "full_size_values" -s > $out/pytest_full.txt 2>&1; echo "rc=$?" >> $out/pytest_full.txt ;;
+    gputests) timeout 2400 python -m pytest tests -x -q -m gpu > $out/pytest_gpu.txt 2>&1; echo "rc=$?" >> $out/pytest_gpu.txt ;;
+    bench_cc) PF_COL_IMPL=cc timeout 600 python bench.py --steps 5 --no-cpu-baseline > $out/bench_cc.json 2> $out/bench_cc.err ;;
+    bench_tc) timeout 600 python bench.py --steps 5 --no-cpu-baseline > $out/bench_tc.json 2> $out/bench_tc.err ;;
+    bench)   timeout 900 python bench.py > $out/bench.json 2> $out/bench.err ;;
+    smoke)   timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke.txt 2>&1; echo "rc=$?" >> $out/smoke.txt ;;
+    *) echo "unknown step $step" ;;
+  esac
+done
+tail -n 5 $out/*.txt 2>/dev/null
+for f in $out/bench*.json; do [ -f "$f" ] && python - "$f" <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    k=d["roofline"]["kernels"]
+    print(sys.argv[1], "ms/step %.2f"%d["ms_per_step"], "e2e %.2f"%d["e2e"]["ms_per_step"], {a:round(b["ms_per_step"],2) for a,b in k.items()})
+except Exception as e:
+    print(sys.argv[1], "unreadable:", e)
+PY
+done
