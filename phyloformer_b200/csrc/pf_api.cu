@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -44,6 +45,7 @@ struct Plan {  // workspace carve-up for one (B, n, L, pair range)
   long long Pl, P;
   int n_chunks, ppc;        // k_col_partial (FFMA): pair chunks
   int n_chunks_tc, ppc_tc;  // k_col_partial_tc (tcgen05): pair chunks, ppc_tc a multiple of 32
+  int n_chunks_ws, ppc_ws;  // k_col_partial_ws (tcgen05, warp specialised, one CTA per SM)
   size_t off_x, off_part, off_colsum, off_colM, off_semb, off_qc, total;
 };
 
@@ -57,7 +59,8 @@ struct pf_ctx {
   PfFfnTcW* tc_dev = nullptr;   // [nb] bf16 hi/lo smem images for the tcgen05 FFN
   PfFfnTcW* tc16_dev = nullptr; // [nb] the same in fp16 (PF_PREC_FP16)
   PfAttnTcW* atc_dev = nullptr; // [nb][2] q/k weight images for the tcgen05 attention kernels (0: row, 1: column)
-  int col_impl = 1;             // 0: k_col_partial (FFMA), 1: k_col_partial_tc (tcgen05); env PF_COL_IMPL=cc|tc
+  int col_impl = 2;             // 0: k_col_partial (FFMA), 1: k_col_partial_tc (tcgen05, one thread per token),
+                                // 2: k_col_partial_ws (tcgen05, warp specialised); env PF_COL_IMPL=cc|tc1|tc
   std::vector<PfFfnConst> ffn_const;  // [nb] host copies passed as __grid_constant__ kernel parameters
   int launches = 0;
   int ffn_impl = 1;             // 0: pf_ffn_tc.cuh (phased), 1: pf_ffn_ws.cuh (warp-specialised); env PF_FFN_IMPL=tc|ws
@@ -124,28 +127,27 @@ Plan make_plan(const pf_ctx* h, int B, int n, int L, long long lo, long long hi)
   if (p.ppc < 1) p.ppc = 1;
   p.n_chunks = (int)((p.Pl + p.ppc - 1) / p.ppc);
   if (p.n_chunks < 1) p.n_chunks = 1;
-  {  // tensor-core variant: units = (msa, 4-site window, chunk), two 128-thread CTAs per SM walk over them;
-     // cost = rounds x (tiles per unit + per-unit epilogue, about 3 tiles' worth)
-    const long long win = (long long)B * ((L + 3) / 4), slots2 = 2LL * h->n_sm;
-    long long bnc = 1, bcost = -1;
+  // tensor-core variants: units = (msa, 4-site window, chunk) walked by `slots` persistent CTAs;
+  // cost = rounds x (tiles per unit + per-unit epilogue, about 3 tiles' worth)
+  auto pick = [&](long long slots, int* ppc_out, int* nc_out) {
+    const long long win = (long long)B * ((L + 3) / 4);
+    long long bppc = 32, bcost = -1;
     for (long long nc = 1; nc <= 64; ++nc) {
       long long ppc = (p.Pl + nc - 1) / nc;
       ppc = (ppc + 31) / 32 * 32;
       if (ppc < 32) ppc = 32;
       const long long chunks = (p.Pl + ppc - 1) / ppc;
-      if (chunks < nc && nc > 1) continue;   // same partition as a smaller nc
-      const long long rounds = (win * chunks + slots2 - 1) / slots2;
+      const long long rounds = (win * chunks + slots - 1) / slots;
       const long long cost = rounds * (ppc / 32 + 3) * 64 + chunks;
-      if (bcost < 0 || cost < bcost) { bcost = cost; bnc = nc; }
+      if (bcost < 0 || cost < bcost) { bcost = cost; bppc = ppc; }
     }
-    long long ppc = (p.Pl + bnc - 1) / bnc;
-    ppc = (ppc + 31) / 32 * 32;
-    if (ppc < 32) ppc = 32;
-    p.ppc_tc = (int)ppc;
-    p.n_chunks_tc = (int)((p.Pl + ppc - 1) / ppc);
-    if (p.n_chunks_tc < 1) p.n_chunks_tc = 1;
-  }
-  const int max_chunks = p.n_chunks > p.n_chunks_tc ? p.n_chunks : p.n_chunks_tc;
+    *ppc_out = (int)bppc;
+    *nc_out = (int)((p.Pl + bppc - 1) / bppc);
+    if (*nc_out < 1) *nc_out = 1;
+  };
+  pick(2LL * h->n_sm, &p.ppc_tc, &p.n_chunks_tc);
+  pick((long long)h->n_sm, &p.ppc_ws, &p.n_chunks_ws);
+  const int max_chunks = std::max(p.n_chunks, std::max(p.n_chunks_tc, p.n_chunks_ws));
   size_t off = 0;
   p.off_x = off;       off = align_up(off + (size_t)B * p.Pl * L * PF_D * sizeof(float), 256);
   p.off_part = off;    off = align_up(off + (size_t)max_chunks * B * L * PF_PART * sizeof(float), 256);
@@ -316,7 +318,7 @@ int pf_create(pf_handle* out, const pf_cfg* cfg, const float* const* weights_dev
   if (const char* e_impl = getenv("PF_FFN_IMPL")) h->ffn_impl = (strcmp(e_impl, "tc") == 0) ? 0 : 1;
   if (const char* e_row = getenv("PF_ROW_IMPL")) h->row_impl = (strcmp(e_row, "ld") == 0) ? 0 : 1;
   if (const char* e_prof = getenv("PF_WS_PROF")) h->ws_prof = atoi(e_prof);
-  if (const char* e_col = getenv("PF_COL_IMPL")) h->col_impl = (strcmp(e_col, "cc") == 0) ? 0 : 1;
+  if (const char* e_col = getenv("PF_COL_IMPL")) h->col_impl = (strcmp(e_col, "cc") == 0) ? 0 : (strcmp(e_col, "tc1") == 0) ? 1 : 2;
   int rc = pf_ffn_tc_init();
   if (rc == 0) rc = pf_ffn_ws_init();
   if (rc == 0) rc = pf_attn_tc_init();
@@ -439,9 +441,15 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
     // ---- column attention summaries ----
     const bool apply_only = dbg && (n_stages == 3 * b + 2);
     // tensor-core summaries (and the q~ cache the FFN kernel then reads) in every mode but the fp32 one
-    const bool col_tc = h->col_impl == 1 && h->cfg.precision != PF_PREC_FP32 && h->ffn_impl == 1;
+    const bool col_tc = h->col_impl >= 1 && h->cfg.precision != PF_PREC_FP32 && h->ffn_impl == 1;
     {
-      if (col_tc) {
+      if (col_tc && h->col_impl == 2) {
+        const long long units = (long long)B * ((L + 3) / 4) * pl.n_chunks_ws;
+        const int g = (int)(units < (long long)h->n_sm ? units : (long long)h->n_sm);
+        Timed t_(h, PF_KC_COLSUM, st);
+        k_col_partial_ws<<<g, C2_THREADS, C2_SMEM_BYTES, st>>>(h->atc_dev + 2 * b + 1, x, part, qcache, B, L, (int)pl.Pl,
+                                                              pl.ppc_ws, pl.n_chunks_ws, h->err_dev);
+      } else if (col_tc) {
         const long long units = (long long)B * ((L + 3) / 4) * pl.n_chunks_tc;
         const int g = (int)(units < 2LL * h->n_sm ? units : 2LL * h->n_sm);
         Timed t_(h, PF_KC_COLSUM, st);
@@ -452,7 +460,7 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
         Timed t_(h, PF_KC_COLSUM, st);
         k_col_partial<<<g, 256, 0, st>>>(&bw->col, x, part, L, (int)pl.Pl, pl.ppc);
       }
-      const int n_part = col_tc ? pl.n_chunks_tc : pl.n_chunks;
+      const int n_part = !col_tc ? pl.n_chunks : h->col_impl == 2 ? pl.n_chunks_ws : pl.n_chunks_tc;
       // column reduce/finalize: spc sites per CTA (weights stay in registers across them), about
       // two CTAs per SM when there are few sites, PF_FS per CTA for batches of small alignments
       const int n_sites = B * L;

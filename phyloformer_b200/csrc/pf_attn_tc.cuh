@@ -333,6 +333,308 @@ k_col_partial_tc(const PfAttnTcW* __restrict__ Wt, const float* __restrict__ x, 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(CT_TM_COLS) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------
+// k_col_partial_ws: the same computation, warp specialised and persistent (one CTA per SM):
+//   warp 21        LOADER   per tile 32 bulk copies (cp.async.bulk, TMA engine, mbarrier completion) of the
+//                           1 KB [4 sites][64] segment of each pair into a 3-stage shared-memory ring
+//   warps 0..15    P1       8 lanes per token (coalesced LDS.128, 3-step butterflies, ~50 registers):
+//                           LayerNorm, bf16 hi/lo split, operand image (3-deep ring); warp w owns pairs 2w, 2w+1
+//   warp 20        MMA      one elected lane issues QK(n+1) and S(n) (see the header of this file)
+//   warps 16..19   P2       TMEM lane quadrant q = site q, lane = pair: q~, k~ from D_qk, phi, running sums,
+//                           q~ cache, k~ operand; at the end of a work unit D_S -> part
+// (k_col_partial_tc above, one thread per token and everything in program order, is kept as the
+//  readable restatement and A/B partner: PF_COL_IMPL=tc1.)
+// ------------------------------------------------------------------------------------------
+#define C2_NP1 16
+#define C2_THREADS (22 * 32)
+#define C2_NS 3                                   // ring depth (staging, operand image, k~ operand, D_qk)
+#define C2_OFF_A1 0
+#define C2_OFF_XS (C2_NS * AT_A1_BYTES)           // [C2_NS][32 pairs][4 sites][64] fp32
+#define C2_OFF_KT (C2_OFF_XS + C2_NS * 32768)
+#define C2_OFF_BQ (C2_OFF_KT + C2_NS * AT_KT_BYTES)
+#define C2_OFF_RED (C2_OFF_BQ + 4096)             // [4 sites][4 heads][64] floats
+#define C2_OFF_BAR (C2_OFF_RED + 4096)
+#define C2_OFF_TMEM (C2_OFF_BAR + 256)
+#define C2_SMEM_BYTES (C2_OFF_TMEM + 32 + 1024)
+#define C2_TM_COLS 256
+#define C2_TM_S 128                               // D_S[parity][site] at column 128 + 64 parity + 16 site; D_qk[i] at 16 i
+// barrier indices
+#define C2_B_XFULL 0
+#define C2_B_XFREE 3
+#define C2_B_A1FULL 6
+#define C2_B_A1FREE 9
+#define C2_B_QKDONE 12
+#define C2_B_KTFULL 15
+#define C2_B_DSFULL 18
+#define C2_B_DSFREE 20
+
+struct C2Iter {   // the CTA's tile stream: units (chunk, msa, window) strided over the grid, tiles within a unit
+  int B, L, Pl, ppc, nW;
+  long long upc, n_units, u;
+  int chunk, b, w, t, nt, np_last;
+  __device__ __forceinline__ void load_unit() {
+    chunk = (int)(u / upc);
+    const int rem = (int)(u - (long long)chunk * upc);
+    b = rem / nW;
+    w = rem - b * nW;
+    const int p0 = chunk * ppc, p1 = min(Pl, p0 + ppc);
+    nt = (p1 - p0 + 31) >> 5;
+    np_last = (p1 - p0) - 32 * (nt - 1);
+    t = 0;
+  }
+  __device__ __forceinline__ bool init(int B_, int L_, int Pl_, int ppc_, int n_chunks) {
+    B = B_; L = L_; Pl = Pl_; ppc = ppc_; nW = (L + 3) >> 2;
+    upc = (long long)B * nW; n_units = upc * n_chunks; u = blockIdx.x;
+    if (u >= n_units) return false;
+    load_unit();
+    return true;
+  }
+  __device__ __forceinline__ bool next() {     // false at the end of the stream
+    if (++t < nt) return true;
+    u += gridDim.x;
+    if (u >= n_units) return false;
+    load_unit();
+    return true;
+  }
+  __device__ __forceinline__ int n_pairs() const { return t + 1 < nt ? 32 : np_last; }     // valid pairs of this tile
+  __device__ __forceinline__ int n_sites() const { return min(4, L - 4 * w); }
+  __device__ __forceinline__ size_t first_tok() const { return ((size_t)b * Pl + chunk * ppc + 32 * t) * L + 4 * w; }
+};
+
+__global__ void __launch_bounds__(C2_THREADS, 1)
+k_col_partial_ws(const PfAttnTcW* __restrict__ Wt, const float* __restrict__ x, float* __restrict__ part,
+                 float* __restrict__ qcache, int B, int L, int Pl, int ppc, int n_chunks, int* __restrict__ err_flag) {
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const uint32_t sbase = smem_u32(sm);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t bars = sbase + C2_OFF_BAR;
+  auto BAR = [&](int i) { return bars + 8u * (uint32_t)i; };
+
+  for (int i = tid; i < 4096 / 16; i += C2_THREADS)
+    reinterpret_cast<int4*>(sm + C2_OFF_BQ)[i] = reinterpret_cast<const int4*>(Wt->wqk_hi)[i];
+  for (int i = tid; i < C2_NS * AT_KT_BYTES / 16; i += C2_THREADS) reinterpret_cast<int4*>(sm + C2_OFF_KT)[i] = make_int4(0, 0, 0, 0);
+  if (tid == 0) {
+    for (int i = 0; i < C2_NS; ++i) {
+      mbar_init(BAR(C2_B_XFULL + i), 1);
+      mbar_init(BAR(C2_B_XFREE + i), C2_NP1 * 32);
+      mbar_init(BAR(C2_B_A1FULL + i), C2_NP1 * 32);
+      mbar_init(BAR(C2_B_A1FREE + i), 1);
+      mbar_init(BAR(C2_B_QKDONE + i), 1);
+      mbar_init(BAR(C2_B_KTFULL + i), 128);
+    }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(C2_B_DSFULL + i), 1); mbar_init(BAR(C2_B_DSFREE + i), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 20) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + C2_OFF_TMEM), "r"(C2_TM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + C2_OFF_TMEM);
+  bool ok = true;
+  C2Iter it;
+  const bool any = it.init(B, L, Pl, ppc, n_chunks);
+
+  if (warp == 21) {
+    // =============================== LOADER ===============================================
+    if (any) {
+      int n = 0;
+      do {
+        const int st = n % C2_NS;
+        ok = mbar_wait(BAR(C2_B_XFREE + st), (uint32_t)(((n / C2_NS) & 1) ^ 1)) && ok;
+        const int np = it.n_pairs();
+        const uint32_t seg = (uint32_t)it.n_sites() * 256u;
+        if (lane == 0)
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(BAR(C2_B_XFULL + st)), "r"(seg * (uint32_t)np) : "memory");
+        __syncwarp();
+        if (lane < np) {
+          const float* src = x + (it.first_tok() + (size_t)lane * L) * PF_D;
+          const uint32_t dst = sbase + C2_OFF_XS + st * 32768 + lane * 1024;
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(dst), "l"(src), "r"(seg), "r"(BAR(C2_B_XFULL + st)) : "memory");
+        }
+        ++n;
+      } while (it.next());
+    }
+  } else if (warp < C2_NP1) {
+    // =============================== P1: LayerNorm + split ================================
+    const int j = lane & 7, k = lane >> 3;   // lane j of token slot k (= site k of the pair)
+    if (any) {
+      int n = 0;
+      do {
+        const int st = n % C2_NS;
+        const uint32_t ph = (uint32_t)((n / C2_NS) & 1);
+        const int np = it.n_pairs(), ns = it.n_sites();
+        ok = mbar_wait(BAR(C2_B_XFULL + st), ph) && ok;
+        ok = mbar_wait(BAR(C2_B_A1FREE + st), ph ^ 1) && ok;
+        unsigned char* a1 = sm + C2_OFF_A1 + st * AT_A1_BYTES;
+        const unsigned char* xs = sm + C2_OFF_XS + st * 32768;
+#pragma unroll
+        for (int i2 = 0; i2 < 2; ++i2) {
+          const int g = 2 * warp + i2, r = 32 * k + g;
+          float xv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) xv[i] = 0.f;
+          if (g < np && k < ns) load_tok(reinterpret_cast<const float*>(xs + g * 1024 + k * 256), j, xv);
+          float nv[8];
+          ln_normalize<true>(xv, nv);
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) split2(pk2(nv[2 * i], nv[2 * i + 1]), hi[i], lo[i]);
+          // channels 4j..4j+3 -> 16-byte chunk j>>1 (half j&1); 32+4j.. -> chunk 4+(j>>1)
+          const uint32_t rowoff = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+          const uint32_t o0 = rowoff + ((((j >> 1)) ^ (r & 7)) << 4) + (j & 1) * 8;
+          const uint32_t o1 = rowoff + (((4 + (j >> 1)) ^ (r & 7)) << 4) + (j & 1) * 8;
+          *reinterpret_cast<uint2*>(a1 + o0) = make_uint2(hi[0], hi[1]);
+          *reinterpret_cast<uint2*>(a1 + o1) = make_uint2(hi[2], hi[3]);
+          *reinterpret_cast<uint2*>(a1 + 16384 + o0) = make_uint2(lo[0], lo[1]);
+          *reinterpret_cast<uint2*>(a1 + 16384 + o1) = make_uint2(lo[2], lo[3]);
+        }
+        mbar_arrive(BAR(C2_B_XFREE + st));
+        fence_proxy_async_smem();
+        mbar_arrive(BAR(C2_B_A1FULL + st));
+        ++n;
+      } while (it.next());
+    }
+  } else if (warp == 20) {
+    // =============================== MMA ISSUER ===========================================
+    if (any) {
+      C2Iter nx = it;                 // runs one tile ahead: QK(n+1) is issued before S(n)
+      bool has_next = true;
+      int n = 0, unit_count = 0;
+      ok = mbar_wait(BAR(C2_B_A1FULL + 0), 0) && ok;
+      tc_fence_after();
+      if (elect_one()) { at_issue_qk(sbase + C2_OFF_A1, sbase + C2_OFF_BQ, tmem); tc_commit(BAR(C2_B_QKDONE + 0)); }
+      __syncwarp();
+      do {
+        const int st = n % C2_NS, par = unit_count & 1;
+        const bool first = it.t == 0, last = it.t + 1 == it.nt;
+        if (has_next) has_next = nx.next();
+        if (has_next) {
+          const int s1 = (n + 1) % C2_NS;
+          ok = mbar_wait(BAR(C2_B_A1FULL + s1), (uint32_t)((((n + 1) / C2_NS)) & 1)) && ok;
+          tc_fence_after();
+          if (elect_one()) {
+            at_issue_qk(sbase + C2_OFF_A1 + s1 * AT_A1_BYTES, sbase + C2_OFF_BQ, tmem + 16 * s1);
+            tc_commit(BAR(C2_B_QKDONE + s1));
+          }
+          __syncwarp();
+        }
+        ok = mbar_wait(BAR(C2_B_KTFULL + st), (uint32_t)((n / C2_NS) & 1)) && ok;
+        if (first) ok = mbar_wait(BAR(C2_B_DSFREE + par), (uint32_t)(((unit_count >> 1) & 1) ^ 1)) && ok;
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int s = 0; s < 4; ++s)
+            at_issue_s(sbase + C2_OFF_A1 + st * AT_A1_BYTES, sbase + C2_OFF_KT + st * AT_KT_BYTES,
+                       tmem + C2_TM_S + 64 * par + 16 * s, 32 * s, 2, !first);
+          tc_commit(BAR(C2_B_A1FREE + st));
+          if (last) tc_commit(BAR(C2_B_DSFULL + par));
+        }
+        __syncwarp();
+        if (last) ++unit_count;
+        ++n;
+      } while (it.next());
+    }
+  } else if (warp >= 16 && warp < 20) {
+    // =============================== P2: phi, sums, k~ operand, unit epilogue ==============
+    const int q = warp - 16, ptid = tid - 16 * 32;   // site q, row = TMEM lane = 32 q + lane
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    float bq[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bq[i] = Wt->bqk[i];
+    float* red = reinterpret_cast<float*>(sm + C2_OFF_RED);
+    if (any) {
+      int n = 0, unit_count = 0;
+      float ks[PF_H] = {0.f, 0.f, 0.f, 0.f}, qs[PF_H] = {0.f, 0.f, 0.f, 0.f};
+      do {
+        const int st = n % C2_NS;
+        const bool valid = lane < it.n_pairs() && q < it.n_sites();
+        ok = mbar_wait(BAR(C2_B_QKDONE + st), (uint32_t)((n / C2_NS) & 1)) && ok;
+        tc_fence_after();
+        uint32_t v[8];
+        tmem_ld8(tmem + lane_base + 16 * st, v);
+        tc_wait_ld();
+        float kq[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) kq[i] = valid ? phi_elu1(__uint_as_float(v[i]) + bq[i]) : 0.f;
+#pragma unroll
+        for (int h = 0; h < PF_H; ++h) { ks[h] += kq[h]; qs[h] += kq[4 + h]; }
+        if (valid) {
+          const size_t tok = it.first_tok() + (size_t)lane * L + q;
+          *reinterpret_cast<float4*>(qcache + tok * 4) = make_float4(kq[4], kq[5], kq[6], kq[7]);
+        }
+        at_store_kt(sm + C2_OFF_KT + st * AT_KT_BYTES, ptid, kq);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(BAR(C2_B_KTFULL + st));
+        if (it.t + 1 == it.nt) {     // unit end: D_S -> part
+          const int par = unit_count & 1;
+          ok = mbar_wait(BAR(C2_B_DSFULL + par), (uint32_t)((unit_count >> 1) & 1)) && ok;
+          tc_fence_after();
+          float val[4][PF_H];
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            uint32_t d[8];
+            tmem_ld8(tmem + lane_base + C2_TM_S + 64 * par + 16 * s, d);
+            tc_wait_ld();
+#pragma unroll
+            for (int h = 0; h < PF_H; ++h) val[s][h] = __uint_as_float(d[h]) + __uint_as_float(d[4 + h]);
+          }
+          tc_fence_before();
+          mbar_arrive(BAR(C2_B_DSFREE + par));
+          if (ptid >= 64) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+#pragma unroll
+              for (int h = 0; h < PF_H; ++h) red[(s * PF_H + h) * 64 + (ptid - 64)] = val[s][h];
+          }
+#pragma unroll
+          for (int h = 0; h < PF_H; ++h) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              ks[h] += __shfl_xor_sync(PF_FULL, ks[h], o);
+              qs[h] += __shfl_xor_sync(PF_FULL, qs[h], o);
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          float* obase = part + (((size_t)it.chunk * B + it.b) * L + (size_t)4 * it.w) * PF_PART;
+          if (ptid < 64) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+              if (4 * it.w + s < L) {
+#pragma unroll
+                for (int h = 0; h < PF_H; ++h)
+                  obase[(size_t)s * PF_PART + 8 + h * PF_D + ptid] = val[s][h] + red[(s * PF_H + h) * 64 + ptid];
+              }
+            }
+          }
+          if (lane == 0 && 4 * it.w + q < L) {
+            float* o = obase + (size_t)q * PF_PART;
+#pragma unroll
+            for (int h = 0; h < PF_H; ++h) { o[h] = ks[h]; o[4 + h] = qs[h]; }
+          }
+#pragma unroll
+          for (int h = 0; h < PF_H; ++h) { ks[h] = 0.f; qs[h] = 0.f; }
+          asm volatile("bar.sync 1, 128;" ::: "memory");   // red is free again
+          ++unit_count;
+        }
+        ++n;
+      } while (it.next());
+    }
+  }
+  if (!ok && err_flag != nullptr) *err_flag = 5;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 20) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(C2_TM_COLS) : "memory");
+}
+
 inline int pf_attn_tc_init() {
-  return (int)cudaFuncSetAttribute(k_col_partial_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_BYTES);
+  int rc = (int)cudaFuncSetAttribute(k_col_partial_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_BYTES);
+  if (rc == 0) rc = (int)cudaFuncSetAttribute(k_col_partial_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM_BYTES);
+  return rc;
 }
