@@ -23,6 +23,31 @@ namespace {
 
 thread_local char g_err[512] = "";
 
+// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
+typedef CUresult (*pf_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+pf_encode_tiled_fn get_encode_tiled() {
+  static pf_encode_tiled_fn fn = []() -> pf_encode_tiled_fn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return (pf_encode_tiled_fn)p;
+  }();
+  return fn;
+}
+// Tensor map of the activation x[(B Pl) pairs][L sites][64] fp32 with a [32 pairs][4 sites][64] box.
+bool make_x_tensor_map(CUtensorMap* tm, const float* x, long long rows, int L) {
+  pf_encode_tiled_fn enc = get_encode_tiled();
+  if (!enc) return false;
+  const cuuint64_t dims[3] = {PF_D, (cuuint64_t)L, (cuuint64_t)rows};
+  const cuuint64_t strides[2] = {PF_D * sizeof(float), (cuuint64_t)L * PF_D * sizeof(float)};
+  const cuuint32_t box[3] = {PF_D, 4, 32}, estr[3] = {1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -414,6 +439,10 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
     k_embed_sequences<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(h->head_dev, x_dev, not_onehot_dev, B, L, n, semb);
   }
   const int* flag = (x_dev != nullptr) ? not_onehot_dev : nullptr;
+  alignas(64) CUtensorMap x_tmap;
+  memset(&x_tmap, 0, sizeof(x_tmap));
+  if (h->cfg.precision != PF_PREC_FP32 && !make_x_tensor_map(&x_tmap, x, (long long)rows, L))
+    return fail(PF_ERR_CUDA, "pf_forward: cuTensorMapEncodeTiled failed (driver too old for TMA tensor maps?)");
 
   for (int b = 0; b < nb; ++b) {
     const PfBlockW* bw = h->blk_dev + b;
@@ -447,7 +476,7 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
         const long long units = (long long)B * ((L + 3) / 4) * pl.n_chunks_ws;
         const int g = (int)(units < (long long)h->n_sm ? units : (long long)h->n_sm);
         Timed t_(h, PF_KC_COLSUM, st);
-        k_col_partial_ws<<<g, C2_THREADS, C2_SMEM_BYTES, st>>>(h->atc_dev + 2 * b + 1, x, part, qcache, B, L, (int)pl.Pl,
+        k_col_partial_ws<<<g, C2_THREADS, C2_SMEM_BYTES, st>>>(x_tmap, h->atc_dev + 2 * b + 1, part, qcache, B, L, (int)pl.Pl,
                                                               pl.ppc_ws, pl.n_chunks_ws, h->err_dev);
       } else if (col_tc) {
         const long long units = (long long)B * ((L + 3) / 4) * pl.n_chunks_tc;

@@ -17,6 +17,8 @@
 // What is left on the CUDA cores per token: LayerNorm statistics, the bf16 split (shared by both
 // GEMMs), phi on 8 values.  The fp32 ("exact") precision mode keeps the FFMA kernels of pf_kernels.cuh.
 #pragma once
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "pf_ffn_ws.cuh"
 
 struct PfAttnTcW {             // one attention module: B operand of the QK GEMM
@@ -335,8 +337,10 @@ k_col_partial_tc(const PfAttnTcW* __restrict__ Wt, const float* __restrict__ x, 
 
 // ------------------------------------------------------------------------------------------
 // k_col_partial_ws: the same computation, warp specialised and persistent (one CTA per SM):
-//   warp 21        LOADER   per tile 32 bulk copies (cp.async.bulk, TMA engine, mbarrier completion) of the
-//                           1 KB [4 sites][64] segment of each pair into a 3-stage shared-memory ring
+//   warp 21        LOADER   per tile ONE tensor-map TMA copy (cp.async.bulk.tensor.3d, mbarrier completion) of the
+//                           box [32 pairs][4 sites][64 channels] into a 3-stage shared-memory ring; sites past L
+//                           and pairs past the tensor arrive as zeros (32 per-pair bulk copies serialise in the
+//                           issuing warp, one uniform-register instruction per lane: measured loader-bound)
 //   warps 0..15    P1       8 lanes per token (coalesced LDS.128, 3-step butterflies, ~50 registers):
 //                           LayerNorm, bf16 hi/lo split, operand image (3-deep ring); warp w owns pairs 2w, 2w+1
 //   warp 20        MMA      one elected lane issues QK(n+1) and S(n) (see the header of this file)
@@ -402,7 +406,7 @@ struct C2Iter {   // the CTA's tile stream: units (chunk, msa, window) strided o
 };
 
 __global__ void __launch_bounds__(C2_THREADS, 1)
-k_col_partial_ws(const PfAttnTcW* __restrict__ Wt, const float* __restrict__ x, float* __restrict__ part,
+k_col_partial_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnTcW* __restrict__ Wt, float* __restrict__ part,
                  float* __restrict__ qcache, int B, int L, int Pl, int ppc, int n_chunks, int* __restrict__ err_flag) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -446,17 +450,14 @@ k_col_partial_ws(const PfAttnTcW* __restrict__ Wt, const float* __restrict__ x, 
       do {
         const int st = n % C2_NS;
         ok = mbar_wait(BAR(C2_B_XFREE + st), (uint32_t)(((n / C2_NS) & 1) ^ 1)) && ok;
-        const int np = it.n_pairs();
-        const uint32_t seg = (uint32_t)it.n_sites() * 256u;
-        if (lane == 0)
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(BAR(C2_B_XFULL + st)), "r"(seg * (uint32_t)np) : "memory");
-        __syncwarp();
-        if (lane < np) {
-          const float* src = x + (it.first_tok() + (size_t)lane * L) * PF_D;
-          const uint32_t dst = sbase + C2_OFF_XS + st * 32768 + lane * 1024;
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(dst), "l"(src), "r"(seg), "r"(BAR(C2_B_XFULL + st)) : "memory");
+        if (elect_one()) {   // one 3-D tensor-map copy per tile: box [32 pairs][4 sites][64 channels], out-of-range elements arrive as zeros
+          const uint32_t dst = sbase + C2_OFF_XS + st * 32768, bar = BAR(C2_B_XFULL + st);
+          const int c1 = 4 * it.w, c2 = it.b * Pl + it.chunk * ppc + 32 * it.t;
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(32768u) : "memory");
+          asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                       ::"r"(dst), "l"(&tmap), "r"(0), "r"(c1), "r"(c2), "r"(bar) : "memory");
         }
+        __syncwarp();
         ++n;
       } while (it.next());
     }
@@ -475,7 +476,7 @@ k_col_partial_ws(const PfAttnTcW* __restrict__ Wt, const float* __restrict__ x, 
         const unsigned char* xs = sm + C2_OFF_XS + st * 32768;
 #pragma unroll
         for (int i2 = 0; i2 < 2; ++i2) {
-          const int g = 2 * warp + i2, r = 32 * k + g;
+          const int g = (2 * warp + i2) ^ ((k & 1) << 2), r = 32 * k + g;   // odd slots take the pair 4 away: their 64-byte halves of the operand row land on the other banks
           float xv[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) xv[i] = 0.f;
