@@ -37,15 +37,26 @@ pf_encode_tiled_fn get_encode_tiled() {
   }();
   return fn;
 }
-// Tensor map of the activation x[(B Pl) pairs][L sites][64] fp32 with a [32 pairs][4 sites][64] box.
+// Tensor map of the activation x[(B Pl) pairs][L sites][64] fp32: box [32 pairs][4 sites][32 channels],
+// SWIZZLE_128B (the 16-byte chunks of every 128-byte row XOR-ed with the row index mod 8).
+// 2-D view of the same buffer, x[tokens][64]: box [128 tokens][32 channels], SWIZZLE_128B (row kernel).
+bool make_x_tensor_map_2d(CUtensorMap* tm, const float* x, long long n_tok) {
+  pf_encode_tiled_fn enc = get_encode_tiled();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {PF_D, (cuuint64_t)n_tok};
+  const cuuint64_t strides[1] = {PF_D * sizeof(float)};
+  const cuuint32_t box[2] = {32, 128}, estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 bool make_x_tensor_map(CUtensorMap* tm, const float* x, long long rows, int L) {
   pf_encode_tiled_fn enc = get_encode_tiled();
   if (!enc) return false;
   const cuuint64_t dims[3] = {PF_D, (cuuint64_t)L, (cuuint64_t)rows};
   const cuuint64_t strides[2] = {PF_D * sizeof(float), (cuuint64_t)L * PF_D * sizeof(float)};
-  const cuuint32_t box[3] = {PF_D, 4, 32}, estr[3] = {1, 1, 1};
+  const cuuint32_t box[3] = {32, 4, 32}, estr[3] = {1, 1, 1};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 int fail(int code, const char* fmt, ...) {
@@ -89,7 +100,8 @@ struct pf_ctx {
   std::vector<PfFfnConst> ffn_const;  // [nb] host copies passed as __grid_constant__ kernel parameters
   int launches = 0;
   int ffn_impl = 1;             // 0: pf_ffn_tc.cuh (phased), 1: pf_ffn_ws.cuh (warp-specialised); env PF_FFN_IMPL=tc|ws
-  int row_impl = 1;             // 0: k_row_attn<0> (register loads), 1: k_row_attn_tma (bulk-copy ring); env PF_ROW_IMPL=ld|tma
+  int row_impl = 2;             // 0: k_row_attn<0> (register loads), 1: k_row_attn_tma (bulk-copy ring), 2: k_row_attn_ws
+                                // (tcgen05, warp specialised; tensor-core modes, blocks 1.., L <= 1536); env PF_ROW_IMPL=ld|tma|tc
   // peer-memory exchange (pf_set_peer_exchange): symmetric buffers of all ranks, mapped locally
   int peer_rank = 0, peer_world = 0;
   unsigned char** peers_dev = nullptr;   // [world] device array of buffer base pointers
@@ -341,7 +353,7 @@ int pf_create(pf_handle* out, const pf_cfg* cfg, const float* const* weights_dev
   CUDA_TRY(cudaFuncSetAttribute(k_row_attn<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_TRY(cudaFuncSetAttribute(k_row_attn_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   if (const char* e_impl = getenv("PF_FFN_IMPL")) h->ffn_impl = (strcmp(e_impl, "tc") == 0) ? 0 : 1;
-  if (const char* e_row = getenv("PF_ROW_IMPL")) h->row_impl = (strcmp(e_row, "ld") == 0) ? 0 : 1;
+  if (const char* e_row = getenv("PF_ROW_IMPL")) h->row_impl = (strcmp(e_row, "ld") == 0) ? 0 : (strcmp(e_row, "tma") == 0) ? 1 : 2;
   if (const char* e_prof = getenv("PF_WS_PROF")) h->ws_prof = atoi(e_prof);
   if (const char* e_col = getenv("PF_COL_IMPL")) h->col_impl = (strcmp(e_col, "cc") == 0) ? 0 : (strcmp(e_col, "tc1") == 0) ? 1 : 2;
   int rc = pf_ffn_tc_init();
@@ -408,7 +420,11 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
   if (ws_bytes < pl.total) return fail(PF_ERR_WORKSPACE, "pf_forward: workspace %zu < %zu bytes", ws_bytes, pl.total);
   if ((long long)B * pl.Pl > 0x7fffffffLL) return fail(PF_ERR_ARG, "pf_forward: too many pair rows");
   const size_t row_smem = sizeof(RowSmem) + (size_t)L * 4 * sizeof(float);
-  if (row_smem + RT_STAGES * RT_STAGE_BYTES > 220 * 1024) h->row_impl = 0;  // very long rows: fall back to register loads
+  // implementation of the row kernel for THIS call (blocks 1..): tensor cores when the mode and the row length allow
+  // it, else the bulk-copy ring, else (very long rows) plain register loads
+  int row_impl = h->row_impl;
+  if (row_impl == 2 && (h->cfg.precision == PF_PREC_FP32 || rw_smem_bytes(L) > 227 * 1024)) row_impl = 1;
+  if (row_impl == 1 && row_smem + RT_STAGES * RT_STAGE_BYTES > 220 * 1024) row_impl = 0;
   if (row_smem > 200 * 1024) return fail(PF_ERR_ARG, "pf_forward: L=%d exceeds the row kernel's shared-memory budget", L);
 
   cudaStream_t st = (cudaStream_t)stream;
@@ -441,7 +457,10 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
   const int* flag = (x_dev != nullptr) ? not_onehot_dev : nullptr;
   alignas(64) CUtensorMap x_tmap;
   memset(&x_tmap, 0, sizeof(x_tmap));
-  if (h->cfg.precision != PF_PREC_FP32 && !make_x_tensor_map(&x_tmap, x, (long long)rows, L))
+  alignas(64) CUtensorMap x_tmap2;
+  memset(&x_tmap2, 0, sizeof(x_tmap2));
+  if (h->cfg.precision != PF_PREC_FP32 &&
+      (!make_x_tensor_map(&x_tmap, x, (long long)rows, L) || !make_x_tensor_map_2d(&x_tmap2, x, n_tok)))
     return fail(PF_ERR_CUDA, "pf_forward: cuTensorMapEncodeTiled failed (driver too old for TMA tensor maps?)");
 
   for (int b = 0; b < nb; ++b) {
@@ -458,7 +477,10 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
       if (embed_only) return done();
     } else {
       Timed t_(h, PF_KC_ROW, st);
-      if (h->row_impl == 1)
+      if (row_impl == 2)
+        k_row_attn_ws<<<rows < h->n_sm ? rows : h->n_sm, RW_THREADS, rw_smem_bytes(L), st>>>(x_tmap2, &bw->row, h->atc_dev + 2 * b, x,
+                                                                                          rows, L, h->err_dev);
+      else if (row_impl == 1)
         k_row_attn_tma<<<rows, 256, row_smem + RT_STAGES * RT_STAGE_BYTES, st>>>(&bw->row, x, L);
       else
         k_row_attn<0><<<rows, 256, row_smem, st>>>(&bw->row, h->head_dev, x, nullptr, nullptr, nullptr, n, L, pair_lo,

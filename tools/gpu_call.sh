@@ -10,6 +10,7 @@ for step in "$@"; do
     gputests) timeout 2400 python -m pytest tests -x -q -m gpu > $out/pytest_gpu.txt 2>&1; echo "rc=$?" >> $out/pytest_gpu.txt ;;
     bench_cc) PF_COL_IMPL=cc timeout 600 python bench.py --steps 5 --no-cpu-baseline > $out/bench_cc.json 2> $out/bench_cc.err ;;
     bench_tc) timeout 600 python bench.py --steps 5 --no-cpu-baseline > $out/bench_tc.json 2> $out/bench_tc.err ;;
+    bench_rowtma) PF_ROW_IMPL=tma timeout 600 python bench.py --steps 5 --no-cpu-baseline > $out/bench_rowtma.json 2> $out/bench_rowtma.err ;;
     bench_tc1) PF_COL_IMPL=tc1 timeout 600 python bench.py --steps 5 --no-cpu-baseline > $out/bench_tc1.json 2> $out/bench_tc1.err ;;
     ncu_col) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_col_partial_ws -s 3 -c 1 -o $out/prof_col python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/ncu_col.log 2>&1 ;;
     ncu_row) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_row_attn_ws -s 3 -c 1 -o $out/prof_row python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/ncu_row.log 2>&1 ;;
