@@ -132,23 +132,47 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------
-def cpu_oracle_rate(n, L, threads, repeats=1):
-    """pair.sites/s of the CPU oracle (fp32, torch CPU ops = what the reference runs) on one
-    n x L MSA."""
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def load_reference_forward():
+    """The CPU comparator: (callable x -> distances, kind).
+    kind "reference": the UNMODIFIED reference module (phyloformer/model.py + attention.py, staged byte
+    for byte under baseline/_ref/phyloformer_ref/ by tools/stage_ref.sh -- git-ignored, it travels to
+    the GPU box with the snapshot), built and loaded exactly like reference infer_alns.py:71-86.
+    kind "port": the CPU oracle (oracle/pf_oracle.py), used only when the staged files are absent."""
+    import torch
+    ck = load_weights_sd()
+    if os.path.exists(os.path.join(REF_DIR, "phyloformer_ref", "model.py")):
+        if REF_DIR not in sys.path:
+            sys.path.insert(0, REF_DIR)
+        from phyloformer_ref.model import Phyloformer as RefPhyloformer
+        m = RefPhyloformer(**ck["hyper_parameters"])
+        m.load_state_dict({k.replace("model.", ""): v for k, v in ck["state_dict"].items() if k != "model.seq2pair"},
+                          strict=False)
+        m.eval()
+        return (lambda x: m(x)), "reference", m
+    from oracle import pf_oracle
+    w = pf_oracle.strip_prefix(ck["state_dict"])
+    return (lambda x: pf_oracle.forward(w, x, torch.float32)), "port", None
+
+
+def cpu_ref_rate(n, L, threads, repeats=1):
+    """pair.sites/s of the CPU comparator (fp32, torch CPU ops) on one n x L MSA."""
     import torch
     from oracle import pf_oracle
     torch.set_num_threads(threads)
-    w = pf_oracle.strip_prefix(load_weights_sd()["state_dict"])
+    fwd, kind, _ = load_reference_forward()
     idx = pf_oracle.synth_msa(n, L, seed=1337, kind="uniform")
     x = pf_oracle.msa_to_onehot(idx)
     best = None
     with torch.no_grad():
         for _ in range(repeats):
             t0 = time.perf_counter()
-            pf_oracle.forward(w, x, torch.float32)
+            fwd(x)
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
-    return (n * (n - 1) // 2) * L / best, best
+    return (n * (n - 1) // 2) * L / best, best, kind
 
 
 def pick_cpu_sample(threads, budget_s):
@@ -156,39 +180,43 @@ def pick_cpu_sample(threads, budget_s):
     if os.environ.get("PF_BENCH_CPU_SAMPLE"):               # "taxa x sites", e.g. 8x32 (tests)
         n, L = (int(v) for v in os.environ["PF_BENCH_CPU_SAMPLE"].lower().split("x"))
         return n, L
-    rate, _ = cpu_oracle_rate(16, 128, threads)             # quick probe (~0.2 s)
+    rate, _, _ = cpu_ref_rate(16, 128, threads)             # quick probe (~0.2 s)
     tokens = max(rate * budget_s, 2e4)
-    for n, L in ((64, 500), (48, 400), (40, 250), (30, 200), (20, 200), (16, 128)):
+    for n, L in ((100, 500), (64, 500), (48, 400), (40, 250), (30, 200), (20, 200), (16, 128)):
         if (n * (n - 1) // 2) * L <= tokens:
             return n, L
     return 16, 128
 
 
 def run_reference(args):
-    """--impl reference: the reference algorithm (CPU oracle port; the reference is Python and
-    cannot travel to the GPU box) on the host cores, same metric/config keys."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (the
+    unmodified module from baseline/_ref when staged, else the oracle port), same metric/config keys.
+    The reference cannot hold the full workloads in host memory (~3.5 KB per pair.site: 70 GB at
+    200 x 1000) and refuses n > 200 (model.py:24-28); each step is a bounded sample of the workload --
+    its cost is exactly linear in pairs x sites."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     threads = os.cpu_count() or 1
-    B, n, L = WORKLOADS[args.workload]
     per_step = max(2.0, min(10.0, 200.0 / max(1, args.steps + args.warmup)))
     sn, sL = pick_cpu_sample(threads, per_step)
     from oracle import pf_oracle
     torch.set_num_threads(threads)
-    w = pf_oracle.strip_prefix(load_weights_sd()["state_dict"])
+    fwd, kind, _ = load_reference_forward()
     x = pf_oracle.msa_to_onehot(pf_oracle.synth_msa(sn, sL, seed=1337, kind="uniform"))
     with torch.no_grad():
         for _ in range(args.warmup):
-            pf_oracle.forward(w, x, torch.float32)
+            fwd(x)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            pf_oracle.forward(w, x, torch.float32)
+            fwd(x)
         dt = time.perf_counter() - t0
     tokens = (sn * (sn - 1) // 2) * sL
     val = tokens * args.steps / dt
-    sample = f"{sn} taxa x {sL} sites ({tokens} pair*sites per step), fp32, torch CPU ops"
+    what = ("unmodified reference phyloformer.model.Phyloformer.forward (baseline/_ref)" if kind == "reference"
+            else "CPU oracle port of the reference graph")
+    sample = f"{sn} taxa x {sL} sites ({tokens} pair*sites per step), fp32, torch CPU ops, {what}"
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
@@ -196,7 +224,7 @@ def run_reference(args):
         "config": {"workload": workload_desc(args.workload), "tokens_per_step": tokens, "precision": "fp32",
                    "parallelism": f"host CPU, {threads} threads (rank 0 only)",
                    "sample": f"each step is a bounded sample of the workload: {sample}"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -285,19 +313,86 @@ def run_native(args):
         e1.record()
         barrier()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-        # ---- MSAs/s at 100 x 500 (second half of BASELINE.json's metric), 1 rank ------------
-        msas_per_s = None
-        if rank == 0 and world == 1:
-            i2 = pf_oracle.synth_msa(100, 500, seed=1437).to(dev)
+        # ---- correctness of what was just timed (outside the timed regions) --------------------
+        checks = {}
+        fx = os.path.join(ROOT, "tests", "golden", f"oracle_fullsize_{n}x{L}.npz")
+        if B == 1 and os.path.exists(fx):     # every distance against the pair-chunked fp64 oracle (tests/golden/make_fullsize.py)
+            import numpy as np
+            ref = torch.from_numpy(np.load(fx)["dist"]).to(dev)
+            checks["parity_vs_oracle_fixture_max_rel"] = float(((d[0].double() - ref).abs() / ref).max())
+        if world > 1 and not batch_sharded:
+            # (a) all ranks hold bit-identical gathered results; (b) rank 0 recomputes the forward unsharded
+            mine = d.contiguous().view(torch.int32)
+            allv = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allv, mine)
+            checks["cross_rank_bit_equal"] = bool(all(torch.equal(allv[0], v) for v in allv))
+            model.check_device_error()
+            if rank == 0:
+                model.unshard()
+                d_full = model.forward_idx(idx, squeeze=False)
+                torch.cuda.synchronize()
+                checks["parity_vs_unsharded_max_rel"] = float(((d.double() - d_full.double()).abs() / d_full.double().abs()).max())
+                del d_full
+            barrier()
+            model.shard_pairs(exchange=args.exchange)
+        # ---- MSAs/s at 100 x 500 (second half of BASELINE.json's metric), at every N ---------
+        # replicas: every rank runs its own 100 x 500 alignment (no collective): N x K alignments / max-over-ranks time
+        msas = {}
+        saved_shard = model._shard
+        model.unshard()
+        i2 = pf_oracle.synth_msa(100, 500, seed=1437 + rank).to(dev)
+        for _ in range(3):
+            model.forward_idx(i2)
+        barrier()
+        e0.record()
+        for _ in range(10):
+            model.forward_idx(i2)
+        e1.record()
+        barrier()
+        msas["replicas"] = world * 10 / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
+        if world > 1:     # the same alignment pair-sharded over all ranks (latency of one alignment)
+            model.shard_pairs(exchange=args.exchange)
+            i3 = pf_oracle.synth_msa(100, 500, seed=1437).to(dev)
             for _ in range(3):
-                model.forward_idx(i2)
-            torch.cuda.synchronize()
+                model.forward_idx(i3)
+            barrier()
             e0.record()
             for _ in range(10):
-                model.forward_idx(i2)
+                model.forward_idx(i3)
             e1.record()
-            torch.cuda.synchronize()
-            msas_per_s = 10 / (e0.elapsed_time(e1) * 1e-3)
+            barrier()
+            msas["pair_sharded"] = 10 / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
+        model._shard = saved_shard
+        msas_per_s = msas["replicas"]
+        # ---- the reference module itself, eager PyTorch on this GPU (100 x 500; seq2pair device shim of
+        #      the reference leaves its seq2pair matrix on the CPU, model.py:136,200-201) ----
+        ref_gpu = None
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            try:
+                _, kind, rm = load_reference_forward()
+                if kind == "reference":
+                    rm = rm.to(dev)
+                    rm._set_seq2pair(100)
+                    rm.seq2pair = rm.seq2pair.to(dev)
+                    xr = pf_oracle.msa_to_onehot(pf_oracle.synth_msa(100, 500, seed=1437)).to(dev)
+                    for _ in range(2):
+                        dr = rm(xr)
+                    torch.cuda.synchronize()
+                    e0.record()
+                    for _ in range(5):
+                        dr = rm(xr)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ms_ref = e0.elapsed_time(e1) / 5
+                    ours = model.forward_idx(pf_oracle.synth_msa(100, 500, seed=1437).to(dev))
+                    ref_gpu = {"what": "unmodified reference module, eager PyTorch fp32 on this B200 (seq2pair moved to the device)",
+                               "workload": "100 taxa x 500 sites", "ms_per_forward": ms_ref, "msas_per_s": 1e3 / ms_ref,
+                               "pair_sites_per_s": 4950 * 500 / (ms_ref * 1e-3),
+                               "native_vs_this_max_rel": float(((ours.double() - dr.double()).abs() / dr.double().abs()).max())}
+                    del rm, xr, dr
+                    torch.cuda.empty_cache()
+            except Exception as e:  # noqa: BLE001  (a comparator, not the product)
+                ref_gpu = {"unavailable": repr(e)[:200]}
 
     if rank != 0:
         if world > 1:
@@ -363,14 +458,19 @@ def run_native(args):
         "gpu_launches": launches,
         "roofline": roofline,
     }
-    if msas_per_s is not None:
-        line["msas_per_s_100x500"] = msas_per_s
+    line["msas_per_s_100x500"] = msas_per_s
+    line["msas_100x500"] = {"replicas_msas_per_s": msas["replicas"], "pair_sharded_msas_per_s": msas.get("pair_sharded"),
+                            "note": "replicas: every rank runs its own alignment; pair_sharded: one alignment over all ranks"}
+    line["checks"] = checks
+    if ref_gpu is not None:
+        line["reference_gpu_eager"] = ref_gpu
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         sn, sL = pick_cpu_sample(threads, 15.0)
-        rate, secs = cpu_oracle_rate(sn, sL, threads)
-        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"{sn} taxa x {sL} sites, one forward, {secs:.1f} s, fp32 torch CPU ops"}
+        rate, secs, kind = cpu_ref_rate(sn, sL, threads)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
+                                "sample": f"{sn} taxa x {sL} sites, one forward, {secs:.1f} s, fp32 torch CPU ops, "
+                                          + ("unmodified reference module (baseline/_ref)" if kind == "reference" else "oracle port")}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

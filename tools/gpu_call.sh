@@ -16,6 +16,13 @@ for step in "$@"; do
     ncu_row) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_row_attn_ws -s 3 -c 1 -o $out/prof_row python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/ncu_row.log 2>&1 ;;
     ncu_ffn) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_colapply_ffn_ws -s 3 -c 1 -o $out/prof_ffn python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/ncu_ffn.log 2>&1 ;;
     bench)   timeout 900 python bench.py > $out/bench.json 2> $out/bench.err ;;
+    diag)    timeout 1200 python tools/diag_variants.py > $out/diag.txt 2>&1 ;;
+    diag_rows) timeout 1200 python tools/diag_rows.py > $out/diag_rows.txt 2>&1 ;;
+    sanit_col) PF_COL_IMPL=tc PF_ROW_IMPL=tma timeout 1200 compute-sanitizer --tool memcheck --print-limit 5 python tools/diag_variants.py one 100 500 1 tc tma > $out/sanit_col.txt 2>&1 ;;
+    coredump) ( export CUDA_ENABLE_COREDUMP_ON_EXCEPTION=1 CUDA_ENABLE_LIGHTWEIGHT_COREDUMP=1 CUDA_COREDUMP_FILE=/tmp/pf_core_%p CUDA_COREDUMP_SHOW_PROGRESS=0;
+               timeout 600 python tools/diag_variants.py one ${DIAG_SHAPE:-100 500 1} tc tma > $out/coredump_run.txt 2>&1 );
+             for c in /tmp/pf_core_*; do [ -f "$c" ] && timeout 300 cuda-gdb -batch -ex "target cudacore $c" -ex "info cuda kernels" -ex "info cuda lanes" -ex "bt" -ex "x/6i \$pc" > $out/coredump_gdb.txt 2>&1 && break; done ;;
+    gdbrun)  timeout 900 cuda-gdb -batch -ex run -ex "info cuda kernels" -ex bt -ex "x/6i \$pc" --args python tools/diag_variants.py one ${DIAG_SHAPE:-100 500 1} tc tma > $out/gdbrun.txt 2>&1 ;;
     smoke)   timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke.txt 2>&1; echo "rc=$?" >> $out/smoke.txt ;;
     *) echo "unknown step $step" ;;
   esac
