@@ -390,6 +390,7 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ bool elect_one_converged() { __syncwarp(); return elect_one(); }   // elect.sync needs the whole warp
 // phi(z) = elu(z) + 1 without the libm exp: ex2.approx of min(z,0) log2(e) (relative error < 1e-6, far
 // below the bf16 split of the operands it feeds); branch free.
 __device__ __forceinline__ float phi_fast(float z) {
@@ -521,7 +522,7 @@ k_col_partial_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnTcW* __re
       for (int t = 0; t < un.nt; ++t, ++n) {
         const int st = n % C2_NS;
         ok = mbar_wait(BAR(C2_B_XFREE + st), (uint32_t)(((n / C2_NS) & 1) ^ 1)) && ok;
-        if (elect_one()) {
+        if (elect_one_converged()) {
           const uint32_t dst = sbase + C2_OFF_XS + st * 32768, bar = BAR(C2_B_XFULL + st);
           const int c1 = 4 * un.w, c2 = un.b * Pl + un.chunk * ppc + 32 * t;
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(32768u) : "memory");
@@ -541,11 +542,13 @@ k_col_partial_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnTcW* __re
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
       const Unit un = decode(u);
       for (int t = 0; t < un.nt; ++t, ++n) {
-        if ((n & 1) != grp) continue;
         const int st = n % C2_NS;
         const uint32_t ph = (uint32_t)((n / C2_NS) & 1);
-        const bool valid = g < (t + 1 < un.nt ? 32 : un.np_last) && k < un.ns;
+        // Both groups wait for EVERY tile's data, also the other group's: a stage is reused every 3 tiles, a group
+        // comes back to it every 6, and a parity wait that skips a phase can be satisfied by the wrong one.
         ok = mbar_wait(BAR(C2_B_XFULL + st), ph) && ok;
+        if ((n & 1) != grp) continue;
+        const bool valid = g < (t + 1 < un.nt ? 32 : un.np_last) && k < un.ns;
         ok = mbar_wait(BAR(C2_B_A1FREE + st), ph ^ 1) && ok;
         at_p1_half(sm + C2_OFF_XS + st * 32768, sm + C2_OFF_A1 + st * AT_A1_BYTES, sr, r, hh, valid);
         mbar_arrive(BAR(C2_B_XFREE + st));
@@ -559,7 +562,7 @@ k_col_partial_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnTcW* __re
       int n = 0, unit_count = 0;
       ok = mbar_wait(BAR(C2_B_A1FULL + 0), 0) && ok;
       tc_fence_after();
-      if (elect_one()) { at_issue_qk2(sbase + C2_OFF_A1, sbase + C2_OFF_BQ, tmem); tc_commit(BAR(C2_B_QKDONE + 0)); }
+      if (elect_one_converged()) { at_issue_qk2(sbase + C2_OFF_A1, sbase + C2_OFF_BQ, tmem); tc_commit(BAR(C2_B_QKDONE + 0)); }
       __syncwarp();
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
         const int chunk = u / upc;
@@ -572,7 +575,7 @@ k_col_partial_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnTcW* __re
             const int s1 = (n + 1) % C2_NS;
             ok = mbar_wait(BAR(C2_B_A1FULL + s1), (uint32_t)(((n + 1) / C2_NS) & 1)) && ok;
             tc_fence_after();
-            if (elect_one()) {
+            if (elect_one_converged()) {
               at_issue_qk2(sbase + C2_OFF_A1 + s1 * AT_A1_BYTES, sbase + C2_OFF_BQ, tmem + 16 * s1);
               tc_commit(BAR(C2_B_QKDONE + s1));
             }
@@ -581,7 +584,7 @@ k_col_partial_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnTcW* __re
           ok = mbar_wait(BAR(C2_B_KTFULL + st), (uint32_t)((n / C2_NS) & 1)) && ok;
           if (first) ok = mbar_wait(BAR(C2_B_DSFREE + par), (uint32_t)(((unit_count >> 1) & 1) ^ 1)) && ok;
           tc_fence_after();
-          if (elect_one()) {
+          if (elect_one_converged()) {
 #pragma unroll
             for (int s = 0; s < 4; ++s)
               at_issue_s(sbase + C2_OFF_A1 + st * AT_A1_BYTES, sbase + C2_OFF_KT + st * AT_KT_BYTES,
@@ -793,7 +796,7 @@ k_row_attn_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnW* __restric
     auto load = [&](int i, int t) {
       const int st = nx % RW_NS;
       ok = mbar_wait(BAR(RW_B_XFREE + st), (uint32_t)(((nx / RW_NS) & 1) ^ 1)) && ok;
-      if (elect_one()) {
+      if (elect_one_converged()) {
         const uint32_t dst = sbase + RW_OFF_XS + st * 32768, bar = BAR(RW_B_XFULL + st);
         const long long tok0 = (long long)(blockIdx.x + (long long)i * gridDim.x) * L + 128 * t;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(32768u) : "memory");
@@ -818,9 +821,10 @@ k_row_attn_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnW* __restric
     for (int i = 0; i <= m; ++i)
       for (int k = 0; k < T + lag; ++k) {
         if (i < m && k < T) {            // ---- item A(i, k) ----
+          // (both groups wait for every item's data: a parity wait must not skip a phase of the stage's barrier)
+          ok = mbar_wait(BAR(RW_B_XFULL + nx % RW_NS), (uint32_t)((nx / RW_NS) & 1)) && ok;
           if ((nx & 1) == grp) {
             const int st = nx % RW_NS, ab = na % RW_NA;
-            ok = mbar_wait(BAR(RW_B_XFULL + st), (uint32_t)((nx / RW_NS) & 1)) && ok;
             ok = mbar_wait(BAR(RW_B_A1FREE + ab), (uint32_t)(((na / RW_NA) & 1) ^ 1)) && ok;
             at_p1_half(sm + RW_OFF_XS + st * 32768, sm + RW_OFF_A1 + ab * AT_A1_BYTES, sr, sr, hh, 128 * k + sr < L);
             mbar_arrive(BAR(RW_B_XFREE + st));
@@ -830,9 +834,9 @@ k_row_attn_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnW* __restric
           ++nx; ++na;
         }
         if (i >= 1 && k >= lag) {        // ---- item B(i - 1, k - lag) ----
+          ok = mbar_wait(BAR(RW_B_XFULL + nx % RW_NS), (uint32_t)((nx / RW_NS) & 1)) && ok;
           if ((nx & 1) == grp) {
             const int st = nx % RW_NS, ib = i - 1, t = k - lag, par = ib & 1;
-            ok = mbar_wait(BAR(RW_B_XFULL + st), (uint32_t)((nx / RW_NS) & 1)) && ok;
             ok = mbar_wait(BAR(RW_B_FINDONE + par), (uint32_t)((ib >> 1) & 1)) && ok;
             const float* fin = reinterpret_cast<const float*>(sm + RW_OFF_FIN + par * RW_FIN_BYTES);
             float4 Mr[8];
@@ -882,7 +886,7 @@ k_row_attn_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnW* __restric
       int n = 0;
       ok = mbar_wait(BAR(RW_B_A1FULL + 0), 0) && ok;
       tc_fence_after();
-      if (elect_one()) { at_issue_qk2(sbase + RW_OFF_A1, sbase + RW_OFF_BQ, tmem); tc_commit(BAR(RW_B_QKDONE + 0)); }
+      if (elect_one_converged()) { at_issue_qk2(sbase + RW_OFF_A1, sbase + RW_OFF_BQ, tmem); tc_commit(BAR(RW_B_QKDONE + 0)); }
       __syncwarp();
       for (int i = 0; i < m; ++i) {
         const int par = i & 1;
@@ -892,7 +896,7 @@ k_row_attn_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnW* __restric
             const int a1 = (n + 1) % RW_NA;
             ok = mbar_wait(BAR(RW_B_A1FULL + a1), (uint32_t)(((n + 1) / RW_NA) & 1)) && ok;
             tc_fence_after();
-            if (elect_one()) {
+            if (elect_one_converged()) {
               at_issue_qk2(sbase + RW_OFF_A1 + a1 * AT_A1_BYTES, sbase + RW_OFF_BQ, tmem + 16 * a1);
               tc_commit(BAR(RW_B_QKDONE + a1));
             }
@@ -901,7 +905,7 @@ k_row_attn_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnW* __restric
           ok = mbar_wait(BAR(RW_B_KTFULL + ab), (uint32_t)((n / RW_NA) & 1)) && ok;
           if (t == 0) ok = mbar_wait(BAR(RW_B_DSFREE + par), (uint32_t)(((i >> 1) & 1) ^ 1)) && ok;
           tc_fence_after();
-          if (elect_one()) {
+          if (elect_one_converged()) {
             at_issue_s(sbase + RW_OFF_A1 + ab * AT_A1_BYTES, sbase + RW_OFF_KT + ab * AT_KT_BYTES, tmem + RW_TM_S + 16 * par, 0, 8, t > 0);
             tc_commit(BAR(RW_B_A1FREE + ab));
             if (t + 1 == T) tc_commit(BAR(RW_B_DSFULL + par));
