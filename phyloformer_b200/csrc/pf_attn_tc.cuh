@@ -340,16 +340,16 @@ k_col_partial_tc(const PfAttnTcW* __restrict__ Wt, const float* __restrict__ x, 
 
 // ------------------------------------------------------------------------------------------
 // k_col_partial_ws: the same computation, warp specialised and persistent (one CTA per SM).
-//   warp 25        LOADER   per tile two tensor-map TMA copies (cp.async.bulk.tensor.3d, SWIZZLE_128B, box
+//   warp 17        LOADER   per tile two tensor-map TMA copies (cp.async.bulk.tensor.3d, SWIZZLE_128B, box
 //                           [32 pairs][4 sites][32 channels]; out-of-range elements arrive as zeros) into a
 //                           3-stage ring: stage = [channel half][128 token rows][128 B], 16-byte chunks XOR-
 //                           swizzled by the row, so a thread can read a whole row without bank conflicts
-//   warps 0..15    P1       two groups of 8 warps (group = tile parity).  Two threads per token (lanes l and
-//                           l^16 own the two 32-channel halves): 8 conflict-free LDS.128, LayerNorm statistics
-//                           with one shuffle each, bf16 hi/lo split, 8 STS.128 into the operand image
-//   warp 24        MMA      one elected lane issues QK(n+1) and S(n)
-//   warps 16..19   P2-K     TMEM lane quadrant = site: k~ = phi(k), running sums, k~ operand (bf16 hi/lo)
-//   warps 20..23   P2-Q     q~ = phi(q), running sums, q~ cache (16 B per token) for the FFN kernel's column apply;
+//   warps 0..7     P1       two threads per token (lanes l and l^16 own the two 32-channel halves): 8 conflict-free
+//                           LDS.128, LayerNorm statistics with one shuffle each, bf16 hi/lo split, 8 STS.128
+//                           into the operand image (3-deep ring)
+//   warp 16        MMA      one elected lane issues QK(n+1) and S(n)
+//   warps 8..11    P2-K     TMEM lane quadrant = site: k~ = phi(k), running sums, k~ operand (bf16 hi/lo)
+//   warps 12..15   P2-Q     q~ = phi(q), running sums, q~ cache (16 B per token) for the FFN kernel's column apply;
 //                           at the end of a work unit the K warps turn D_S into the chunk's partial sums
 // Operand row of token (pair g, site k) of a tile: 32 k + ((g + 2k) & 31): a site's tokens are 32
 // consecutive rows (two K = 16 steps of its S GEMM) and 8 consecutive staging rows (2 pairs x 4 sites)
@@ -359,12 +359,12 @@ k_col_partial_tc(const PfAttnTcW* __restrict__ Wt, const float* __restrict__ x, 
 // (k_col_partial_tc above, one thread per token and everything in program order, is kept as the
 //  readable restatement and A/B partner: PF_COL_IMPL=tc1.)
 // ------------------------------------------------------------------------------------------
-#define C2_NP1 16
-#define C2_WK 16
-#define C2_WQ 20
-#define C2_WMMA 24
-#define C2_WLD 25
-#define C2_THREADS (26 * 32)
+#define C2_NP1 8
+#define C2_WK 8
+#define C2_WQ 12
+#define C2_WMMA 16
+#define C2_WLD 17
+#define C2_THREADS (18 * 32)
 #define C2_NS 3                                   // ring depth (staging, operand image, k~ operand, D_qk)
 #define C2_OFF_A1 0
 #define C2_OFF_XS (C2_NS * AT_A1_BYTES)           // [C2_NS][2 halves][128 rows][128 B]
@@ -389,6 +389,26 @@ k_col_partial_tc(const PfAttnTcW* __restrict__ Wt, const float* __restrict__ x, 
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+// Bounded mbarrier wait of the attention kernels: ~65k suspended polls (tens of milliseconds; a legitimate
+// wait is microseconds), and after the first time-out every later wait of the CTA returns at once (the flag
+// lives in shared memory), so a broken pipeline drains in milliseconds instead of seconds per wait.
+__device__ __forceinline__ bool at_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
+  if (*abort_flag) return false;
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 16); ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 1000;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return true;
+  }
+  *abort_flag = 1;
+  return false;
 }
 __device__ __forceinline__ bool elect_one_converged() { __syncwarp(); return elect_one(); }   // elect.sync needs the whole warp
 // phi(z) = elu(z) + 1 without the libm exp: ex2.approx of min(z,0) log2(e) (relative error < 1e-6, far
@@ -484,6 +504,7 @@ k_col_partial_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnTcW* __re
       mbar_init(BAR(C2_B_KTFULL + i), 256);
     }
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(C2_B_DSFULL + i), 1); mbar_init(BAR(C2_B_DSFREE + i), 128); }
+    *reinterpret_cast<volatile int*>(sm + C2_OFF_TMEM + 16) = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == C2_WMMA) {
@@ -495,6 +516,7 @@ k_col_partial_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnTcW* __re
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + C2_OFF_TMEM);
+  volatile int* abortf = reinterpret_cast<volatile int*>(sm + C2_OFF_TMEM + 16);
   bool ok = true;
 
   // The CTA's tile stream: units u = blockIdx.x, + gridDim.x, ... (unit = chunk, msa, 4-site window), tiles
@@ -521,7 +543,7 @@ k_col_partial_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnTcW* __re
       const Unit un = decode(u);
       for (int t = 0; t < un.nt; ++t, ++n) {
         const int st = n % C2_NS;
-        ok = mbar_wait(BAR(C2_B_XFREE + st), (uint32_t)(((n / C2_NS) & 1) ^ 1)) && ok;
+        ok = at_wait(BAR(C2_B_XFREE + st), (uint32_t)(((n / C2_NS) & 1) ^ 1), abortf) && ok;
         if (elect_one_converged()) {
           const uint32_t dst = sbase + C2_OFF_XS + st * 32768, bar = BAR(C2_B_XFULL + st);
           const int c1 = 4 * un.w, c2 = un.b * Pl + un.chunk * ppc + 32 * t;
@@ -536,7 +558,7 @@ k_col_partial_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnTcW* __re
     }
   } else if (warp < C2_NP1) {
     // =============================== P1: LayerNorm + split ================================
-    const int grp = warp >> 3, hh = lane >> 4, sr = 16 * (warp & 7) + (lane & 15);
+    const int hh = lane >> 4, sr = 16 * warp + (lane & 15);
     const int g = sr >> 2, k = sr & 3, r = 32 * k + ((g + 2 * k) & 31);
     int n = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
@@ -544,12 +566,11 @@ k_col_partial_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnTcW* __re
       for (int t = 0; t < un.nt; ++t, ++n) {
         const int st = n % C2_NS;
         const uint32_t ph = (uint32_t)((n / C2_NS) & 1);
-        // Both groups wait for EVERY tile's data, also the other group's: a stage is reused every 3 tiles, a group
-        // comes back to it every 6, and a parity wait that skips a phase can be satisfied by the wrong one.
-        ok = mbar_wait(BAR(C2_B_XFULL + st), ph) && ok;
-        if ((n & 1) != grp) continue;
+        // (every P1 warp processes every tile: a parity wait must see every phase of a stage's barrier -- with two
+        //  warp groups alternating tiles over a 3-stage ring a group skipped phases and could be released by the wrong one)
+        ok = at_wait(BAR(C2_B_XFULL + st), ph, abortf) && ok;
         const bool valid = g < (t + 1 < un.nt ? 32 : un.np_last) && k < un.ns;
-        ok = mbar_wait(BAR(C2_B_A1FREE + st), ph ^ 1) && ok;
+        ok = at_wait(BAR(C2_B_A1FREE + st), ph ^ 1, abortf) && ok;
         at_p1_half(sm + C2_OFF_XS + st * 32768, sm + C2_OFF_A1 + st * AT_A1_BYTES, sr, r, hh, valid);
         mbar_arrive(BAR(C2_B_XFREE + st));
         fence_proxy_async_smem();
@@ -560,7 +581,7 @@ k_col_partial_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnTcW* __re
     // =============================== MMA ISSUER ===========================================
     if (n_units > (int)blockIdx.x) {
       int n = 0, unit_count = 0;
-      ok = mbar_wait(BAR(C2_B_A1FULL + 0), 0) && ok;
+      ok = at_wait(BAR(C2_B_A1FULL + 0), 0, abortf) && ok;
       tc_fence_after();
       if (elect_one_converged()) { at_issue_qk2(sbase + C2_OFF_A1, sbase + C2_OFF_BQ, tmem); tc_commit(BAR(C2_B_QKDONE + 0)); }
       __syncwarp();
@@ -573,7 +594,7 @@ k_col_partial_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnTcW* __re
           const bool first = t == 0, last = t + 1 == nt;
           if (!last || u + (int)gridDim.x < n_units) {   // QK of the next tile of the stream
             const int s1 = (n + 1) % C2_NS;
-            ok = mbar_wait(BAR(C2_B_A1FULL + s1), (uint32_t)(((n + 1) / C2_NS) & 1)) && ok;
+            ok = at_wait(BAR(C2_B_A1FULL + s1), (uint32_t)(((n + 1) / C2_NS) & 1), abortf) && ok;
             tc_fence_after();
             if (elect_one_converged()) {
               at_issue_qk2(sbase + C2_OFF_A1 + s1 * AT_A1_BYTES, sbase + C2_OFF_BQ, tmem + 16 * s1);
@@ -581,8 +602,8 @@ k_col_partial_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnTcW* __re
             }
             __syncwarp();
           }
-          ok = mbar_wait(BAR(C2_B_KTFULL + st), (uint32_t)((n / C2_NS) & 1)) && ok;
-          if (first) ok = mbar_wait(BAR(C2_B_DSFREE + par), (uint32_t)(((unit_count >> 1) & 1) ^ 1)) && ok;
+          ok = at_wait(BAR(C2_B_KTFULL + st), (uint32_t)((n / C2_NS) & 1), abortf) && ok;
+          if (first) ok = at_wait(BAR(C2_B_DSFREE + par), (uint32_t)(((unit_count >> 1) & 1) ^ 1), abortf) && ok;
           tc_fence_after();
           if (elect_one_converged()) {
 #pragma unroll
@@ -623,7 +644,7 @@ k_col_partial_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnTcW* __re
       for (int t = 0; t < un.nt; ++t, ++n) {
         const int st = n % C2_NS;
         const bool valid = g < (t + 1 < un.nt ? 32 : un.np_last) && q < un.ns;
-        ok = mbar_wait(BAR(C2_B_QKDONE + st), (uint32_t)((n / C2_NS) & 1)) && ok;
+        ok = at_wait(BAR(C2_B_QKDONE + st), (uint32_t)((n / C2_NS) & 1), abortf) && ok;
         tc_fence_after();
         uint32_t va[4], vb[4];
         tmem_ld4(tmem + lane_base + 16 * st + c0, va);
@@ -665,7 +686,7 @@ k_col_partial_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnTcW* __re
         for (int h = 0; h < PF_H; ++h) o[h] = sum[h];
       }
       if (is_k) {
-        ok = mbar_wait(BAR(C2_B_DSFULL + par), (uint32_t)((unit_count >> 1) & 1)) && ok;
+        ok = at_wait(BAR(C2_B_DSFULL + par), (uint32_t)((unit_count >> 1) & 1), abortf) && ok;
         tc_fence_after();
         float val[4][PF_H];
 #pragma unroll
@@ -776,6 +797,7 @@ k_row_attn_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnW* __restric
       mbar_init(BAR(RW_B_QSUM + i), 128);    mbar_init(BAR(RW_B_FINDONE + i), 128);
       mbar_init(BAR(RW_B_FINFREE + i), 256 * T);
     }
+    *reinterpret_cast<volatile int*>(sm + RW_OFF_TMEM + 16) = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == C2_WMMA) {
@@ -787,6 +809,7 @@ k_row_attn_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnW* __restric
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + RW_OFF_TMEM);
+  volatile int* abortf = reinterpret_cast<volatile int*>(sm + RW_OFF_TMEM + 16);
   float* qs = reinterpret_cast<float*>(sm + RW_OFF_QS);
   bool ok = true;
 
@@ -795,7 +818,7 @@ k_row_attn_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnW* __restric
     int nx = 0;
     auto load = [&](int i, int t) {
       const int st = nx % RW_NS;
-      ok = mbar_wait(BAR(RW_B_XFREE + st), (uint32_t)(((nx / RW_NS) & 1) ^ 1)) && ok;
+      ok = at_wait(BAR(RW_B_XFREE + st), (uint32_t)(((nx / RW_NS) & 1) ^ 1), abortf) && ok;
       if (elect_one_converged()) {
         const uint32_t dst = sbase + RW_OFF_XS + st * 32768, bar = BAR(RW_B_XFULL + st);
         const long long tok0 = (long long)(blockIdx.x + (long long)i * gridDim.x) * L + 128 * t;
@@ -815,17 +838,16 @@ k_row_attn_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnW* __restric
       }
   } else if (warp < C2_NP1) {
     // =============================== P1: pass A (LN + split) and pass B (apply) ============
-    const int grp = warp >> 3, wi = warp & 7, hh = lane >> 4, sr = 16 * wi + (lane & 15);
+    const int wi = warp, hh = lane >> 4, sr = 16 * wi + (lane & 15);
     const int j = lane & 7, slot = lane >> 3;
     int nx = 0, na = 0;
     for (int i = 0; i <= m; ++i)
       for (int k = 0; k < T + lag; ++k) {
         if (i < m && k < T) {            // ---- item A(i, k) ----
-          // (both groups wait for every item's data: a parity wait must not skip a phase of the stage's barrier)
-          ok = mbar_wait(BAR(RW_B_XFULL + nx % RW_NS), (uint32_t)((nx / RW_NS) & 1)) && ok;
-          if ((nx & 1) == grp) {
+          {
             const int st = nx % RW_NS, ab = na % RW_NA;
-            ok = mbar_wait(BAR(RW_B_A1FREE + ab), (uint32_t)(((na / RW_NA) & 1) ^ 1)) && ok;
+            ok = at_wait(BAR(RW_B_XFULL + st), (uint32_t)((nx / RW_NS) & 1), abortf) && ok;
+            ok = at_wait(BAR(RW_B_A1FREE + ab), (uint32_t)(((na / RW_NA) & 1) ^ 1), abortf) && ok;
             at_p1_half(sm + RW_OFF_XS + st * 32768, sm + RW_OFF_A1 + ab * AT_A1_BYTES, sr, sr, hh, 128 * k + sr < L);
             mbar_arrive(BAR(RW_B_XFREE + st));
             fence_proxy_async_smem();
@@ -834,10 +856,10 @@ k_row_attn_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnW* __restric
           ++nx; ++na;
         }
         if (i >= 1 && k >= lag) {        // ---- item B(i - 1, k - lag) ----
-          ok = mbar_wait(BAR(RW_B_XFULL + nx % RW_NS), (uint32_t)((nx / RW_NS) & 1)) && ok;
-          if ((nx & 1) == grp) {
+          {
             const int st = nx % RW_NS, ib = i - 1, t = k - lag, par = ib & 1;
-            ok = mbar_wait(BAR(RW_B_FINDONE + par), (uint32_t)((ib >> 1) & 1)) && ok;
+            ok = at_wait(BAR(RW_B_XFULL + st), (uint32_t)((nx / RW_NS) & 1), abortf) && ok;
+            ok = at_wait(BAR(RW_B_FINDONE + par), (uint32_t)((ib >> 1) & 1), abortf) && ok;
             const float* fin = reinterpret_cast<const float*>(sm + RW_OFF_FIN + par * RW_FIN_BYTES);
             float4 Mr[8];
             float bo[8];
@@ -884,7 +906,7 @@ k_row_attn_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnW* __restric
     // =============================== MMA ISSUER ===========================================
     if (m > 0) {
       int n = 0;
-      ok = mbar_wait(BAR(RW_B_A1FULL + 0), 0) && ok;
+      ok = at_wait(BAR(RW_B_A1FULL + 0), 0, abortf) && ok;
       tc_fence_after();
       if (elect_one_converged()) { at_issue_qk2(sbase + RW_OFF_A1, sbase + RW_OFF_BQ, tmem); tc_commit(BAR(RW_B_QKDONE + 0)); }
       __syncwarp();
@@ -894,7 +916,7 @@ k_row_attn_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnW* __restric
           const int ab = n % RW_NA;
           if (t + 1 < T || i + 1 < m) {
             const int a1 = (n + 1) % RW_NA;
-            ok = mbar_wait(BAR(RW_B_A1FULL + a1), (uint32_t)(((n + 1) / RW_NA) & 1)) && ok;
+            ok = at_wait(BAR(RW_B_A1FULL + a1), (uint32_t)(((n + 1) / RW_NA) & 1), abortf) && ok;
             tc_fence_after();
             if (elect_one_converged()) {
               at_issue_qk2(sbase + RW_OFF_A1 + a1 * AT_A1_BYTES, sbase + RW_OFF_BQ, tmem + 16 * a1);
@@ -902,8 +924,8 @@ k_row_attn_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnW* __restric
             }
             __syncwarp();
           }
-          ok = mbar_wait(BAR(RW_B_KTFULL + ab), (uint32_t)((n / RW_NA) & 1)) && ok;
-          if (t == 0) ok = mbar_wait(BAR(RW_B_DSFREE + par), (uint32_t)(((i >> 1) & 1) ^ 1)) && ok;
+          ok = at_wait(BAR(RW_B_KTFULL + ab), (uint32_t)((n / RW_NA) & 1), abortf) && ok;
+          if (t == 0) ok = at_wait(BAR(RW_B_DSFREE + par), (uint32_t)(((i >> 1) & 1) ^ 1), abortf) && ok;
           tc_fence_after();
           if (elect_one_converged()) {
             at_issue_s(sbase + RW_OFF_A1 + ab * AT_A1_BYTES, sbase + RW_OFF_KT + ab * AT_KT_BYTES, tmem + RW_TM_S + 16 * par, 0, 8, t > 0);
@@ -942,11 +964,11 @@ k_row_attn_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnW* __restric
       const int par = i & 1;
       const uint32_t rph = (uint32_t)((i >> 1) & 1);
       float sum[PF_H] = {0.f, 0.f, 0.f, 0.f};
-      if (!is_k) ok = mbar_wait(BAR(RW_B_FINFREE + par), rph ^ 1) && ok;    // pass B of row i-2 has read this q~ buffer
+      if (!is_k) ok = at_wait(BAR(RW_B_FINFREE + par), rph ^ 1, abortf) && ok;    // pass B of row i-2 has read this q~ buffer
       for (int t = 0; t < T; ++t, ++n) {
         const int ab = n % RW_NA, site = 128 * t + row;
         const bool valid = site < L;
-        ok = mbar_wait(BAR(RW_B_QKDONE + ab), (uint32_t)((n / RW_NA) & 1)) && ok;
+        ok = at_wait(BAR(RW_B_QKDONE + ab), (uint32_t)((n / RW_NA) & 1), abortf) && ok;
         tc_fence_after();
         uint32_t va[4], vb[4];
         tmem_ld4(tmem + lane_base + 16 * ab + c0, va);
@@ -984,14 +1006,14 @@ k_row_attn_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnW* __restric
         // wsum is rewritten per row: the K warps have read the previous row's values before they arrive on
         // FINDONE, and this row's Q sums are only complete after its last tile, i.e. after that finalize
         // (K and Q warps process tiles in lock step through KTFULL/QKDONE; one row of slack is guarded below)
-        if (i > 0) ok = mbar_wait(BAR(RW_B_FINDONE + (par ^ 1)), (uint32_t)(((i - 1) >> 1) & 1)) && ok;
+        if (i > 0) ok = at_wait(BAR(RW_B_FINDONE + (par ^ 1)), (uint32_t)(((i - 1) >> 1) & 1), abortf) && ok;
         if (lane == 0) {
 #pragma unroll
           for (int h = 0; h < PF_H; ++h) wsum[(4 + q) * 4 + h] = sum[h];
         }
         mbar_arrive(BAR(RW_B_QSUM + par));
       } else {
-        ok = mbar_wait(BAR(RW_B_DSFULL + par), rph) && ok;
+        ok = at_wait(BAR(RW_B_DSFULL + par), rph, abortf) && ok;
         tc_fence_after();
         uint32_t d[8];
         tmem_ld8(tmem + lane_base + RW_TM_S + 16 * par, d);
@@ -1009,8 +1031,8 @@ k_row_attn_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnW* __restric
 #pragma unroll
           for (int h = 0; h < PF_H; ++h) red[h * 64 + (ptid - 64)] = val[h];
         }
-        ok = mbar_wait(BAR(RW_B_QSUM + par), rph) && ok;
-        ok = mbar_wait(BAR(RW_B_FINFREE + par), rph ^ 1) && ok;     // pass B of row i-2 has read M / bo / qinv of this parity
+        ok = at_wait(BAR(RW_B_QSUM + par), rph, abortf) && ok;
+        ok = at_wait(BAR(RW_B_FINFREE + par), rph ^ 1, abortf) && ok;     // pass B of row i-2 has read M / bo / qinv of this parity
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (ptid < 64) {
 #pragma unroll

@@ -5,18 +5,18 @@ out=gpurun_out/$tag; mkdir -p $out
 for step in "$@"; do
   case $step in
     probe)   timeout 120 tools/probe/umma_mn_probe > $out/probe.txt 2>&1; echo "probe rc=$?" >> $out/probe.txt ;;
-    tcattn)  timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "tensor_core_attention or stage_taps or synthetic_shapes" -s > $out/pytest_tcattn.txt 2>&1; echo "rc=$?" >> $out/pytest_tcattn.txt ;;
+    tcattn)  timeout 400 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "tensor_core_attention or stage_taps or synthetic_shapes" -s > $out/pytest_tcattn.txt 2>&1; echo "rc=$?" >> $out/pytest_tcattn.txt ;;
     full)    timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "full_size_values" -s > $out/pytest_full.txt 2>&1; echo "rc=$?" >> $out/pytest_full.txt ;;
     gputests) timeout 2400 python -m pytest tests -x -q -m gpu > $out/pytest_gpu.txt 2>&1; echo "rc=$?" >> $out/pytest_gpu.txt ;;
     bench_cc) PF_COL_IMPL=cc timeout 600 python bench.py --steps 5 --no-cpu-baseline > $out/bench_cc.json 2> $out/bench_cc.err ;;
-    bench_tc) timeout 600 python bench.py --steps 5 --no-cpu-baseline > $out/bench_tc.json 2> $out/bench_tc.err ;;
-    bench_rowtma) PF_ROW_IMPL=tma timeout 600 python bench.py --steps 5 --no-cpu-baseline > $out/bench_rowtma.json 2> $out/bench_rowtma.err ;;
+    bench_tc) timeout 240 python bench.py --steps 5 --no-cpu-baseline > $out/bench_tc.json 2> $out/bench_tc.err ;;
+    bench_rowtma) PF_ROW_IMPL=tma timeout 240 python bench.py --steps 5 --no-cpu-baseline > $out/bench_rowtma.json 2> $out/bench_rowtma.err ;;
     bench_tc1) PF_COL_IMPL=tc1 timeout 600 python bench.py --steps 5 --no-cpu-baseline > $out/bench_tc1.json 2> $out/bench_tc1.err ;;
     ncu_col) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_col_partial_ws -s 3 -c 1 -o $out/prof_col python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/ncu_col.log 2>&1 ;;
     ncu_row) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_row_attn_ws -s 3 -c 1 -o $out/prof_row python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/ncu_row.log 2>&1 ;;
     ncu_ffn) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_colapply_ffn_ws -s 3 -c 1 -o $out/prof_ffn python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/ncu_ffn.log 2>&1 ;;
     bench)   timeout 900 python bench.py > $out/bench.json 2> $out/bench.err ;;
-    diag)    timeout 1200 python tools/diag_variants.py > $out/diag.txt 2>&1 ;;
+    diag)    timeout 600 python tools/diag_variants.py > $out/diag.txt 2>&1 ;;
     diag_rows) timeout 1200 python tools/diag_rows.py > $out/diag_rows.txt 2>&1 ;;
     sanit_col) PF_COL_IMPL=tc PF_ROW_IMPL=tma timeout 1200 compute-sanitizer --tool memcheck --print-limit 5 python tools/diag_variants.py one 100 500 1 tc tma > $out/sanit_col.txt 2>&1 ;;
     coredump) ( export CUDA_ENABLE_COREDUMP_ON_EXCEPTION=1 CUDA_ENABLE_LIGHTWEIGHT_COREDUMP=1 CUDA_COREDUMP_FILE=/tmp/pf_core_%p CUDA_COREDUMP_SHOW_PROGRESS=0;
