@@ -748,8 +748,11 @@ k_col_partial_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnTcW* __re
 #define RW_OFF_XS (RW_NA * AT_A1_BYTES)
 #define RW_OFF_KT (RW_OFF_XS + RW_NS * 32768)
 #define RW_OFF_BQ (RW_OFF_KT + RW_NA * AT_KT_BYTES)
-#define RW_OFF_FIN (RW_OFF_BQ + 2048)             // [2] { M[64][4], bo[64], qinv[4], pad } = 2 x 1536 B
-#define RW_FIN_BYTES 1536
+#define RW_OFF_FIN (RW_OFF_BQ + 2048)             // [2] { M[80][4] (row of channel c at c + c/4: conflict-free for the 8-lane
+                                                  //       layout), bo[64], qinv[4], pad } = 2 x 2048 B
+#define RW_FIN_BYTES 2048
+#define RW_FIN_BO 320
+#define RW_FIN_QINV 384
 #define RW_OFF_SCR (RW_OFF_FIN + 2 * RW_FIN_BYTES)   // finalize scratch: tot[264] ubar[256] ctxp[256] ctx[64] red[256] wsum[32]
 #define RW_SCR_BYTES ((264 + 256 + 256 + 64 + 256 + 32) * 4)
 #define RW_OFF_BAR (RW_OFF_SCR + RW_SCR_BYTES)
@@ -816,25 +819,30 @@ k_row_attn_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnW* __restric
   if (warp == C2_WLD) {
     // =============================== LOADER ===============================================
     int nx = 0;
-    auto load = [&](int i, int t) {
+    // L2 policies: pass-A tiles are read again one row later (pass B) -> evict_last; pass-B tiles are dead after
+    // the read -> evict_first (the result goes out with streaming stores), so the re-read stays an L2 hit
+    unsigned long long pol_keep, pol_drop;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_drop));
+    auto load = [&](int i, int t, unsigned long long pol) {
       const int st = nx % RW_NS;
       ok = at_wait(BAR(RW_B_XFREE + st), (uint32_t)(((nx / RW_NS) & 1) ^ 1), abortf) && ok;
       if (elect_one_converged()) {
         const uint32_t dst = sbase + RW_OFF_XS + st * 32768, bar = BAR(RW_B_XFULL + st);
         const long long tok0 = (long long)(blockIdx.x + (long long)i * gridDim.x) * L + 128 * t;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(32768u) : "memory");
-        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                     ::"r"(dst), "l"(&tmap), "r"(0), "r"((int)tok0), "r"(bar) : "memory");
-        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                     ::"r"(dst + 16384), "l"(&tmap), "r"(32), "r"((int)tok0), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+                     ::"r"(dst), "l"(&tmap), "r"(0), "r"((int)tok0), "r"(bar), "l"(pol) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+                     ::"r"(dst + 16384), "l"(&tmap), "r"(32), "r"((int)tok0), "r"(bar), "l"(pol) : "memory");
       }
       __syncwarp();
       ++nx;
     };
     for (int i = 0; i <= m; ++i)
       for (int k = 0; k < T + lag; ++k) {
-        if (i < m && k < T) load(i, k);
-        if (i >= 1 && k >= lag) load(i - 1, k - lag);
+        if (i < m && k < T) load(i, k, pol_keep);
+        if (i >= 1 && k >= lag) load(i - 1, k - lag, pol_drop);
       }
   } else if (warp < C2_NP1) {
     // =============================== P1: pass A (LN + split) and pass B (apply) ============
@@ -866,10 +874,10 @@ k_row_attn_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnW* __restric
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
               const int ch = chan_of(j, c);
-              Mr[c] = *reinterpret_cast<const float4*>(fin + 4 * ch);
-              bo[c] = fin[256 + ch];
+              Mr[c] = *reinterpret_cast<const float4*>(fin + 4 * (ch + (ch >> 2)));
+              bo[c] = fin[RW_FIN_BO + ch];
             }
-            const float4 qi = *reinterpret_cast<const float4*>(fin + 320);
+            const float4 qi = *reinterpret_cast<const float4*>(fin + RW_FIN_QINV);
             const unsigned char* xs = sm + RW_OFF_XS + st * 32768;
             float* xrow = x + (size_t)(blockIdx.x + (size_t)ib * gridDim.x) * L * PF_D;
 #pragma unroll
@@ -1043,13 +1051,13 @@ k_row_attn_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnW* __restric
           tot[ptid] = ((wsum[(w0 + 0) * 4 + h] + wsum[(w0 + 1) * 4 + h]) + wsum[(w0 + 2) * 4 + h]) + wsum[(w0 + 3) * 4 + h];
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        float* fin = reinterpret_cast<float*>(sm + RW_OFF_FIN + par * RW_FIN_BYTES);   // M[64][4] | bo[64] | qinv[4]
+        float* fin = reinterpret_cast<float*>(sm + RW_OFF_FIN + par * RW_FIN_BYTES);   // M[80][4] | bo[64] | qinv[4]
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int idx = ptid + 128 * e, h = idx >> 6, c = idx & 63;
           ubar[h * PF_D + c] = fmaf(W->gamma[c], tot[8 + h * PF_D + c] / tot[h], W->beta[c]);
         }
-        if (ptid < PF_H) fin[320 + ptid] = (float)L / tot[4 + ptid];
+        if (ptid < PF_H) fin[RW_FIN_QINV + ptid] = (float)L / tot[4 + ptid];
         asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
@@ -1062,7 +1070,7 @@ k_row_attn_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnW* __restric
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (ptid < PF_D) {
           ctx[ptid] = (((W->bv[ptid] + ctxp[ptid]) + ctxp[PF_D + ptid]) + ctxp[2 * PF_D + ptid]) + ctxp[3 * PF_D + ptid];
-          fin[256 + ptid] = W->bo[ptid];
+          fin[RW_FIN_BO + ptid] = W->bo[ptid];
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
@@ -1071,7 +1079,7 @@ k_row_attn_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnW* __restric
           float acc = 0.f;
 #pragma unroll
           for (int ee = 0; ee < PF_DH; ++ee) acc = fmaf(W->wo[c][h * PF_DH + ee], ctx[h * PF_DH + ee], acc);
-          fin[c * 4 + h] = acc;
+          fin[(c + (c >> 2)) * 4 + h] = acc;
         }
         mbar_arrive(BAR(RW_B_FINDONE + par));
       }
