@@ -136,6 +136,9 @@ def write_outputs(out_dir, chunk, mats, nj):
     return len(chunk)
 
 
+MAX_BATCH = 65535  # alignments per batched call: the batch index is a gridDim.y/z of several kernels
+
+
 def run_pipeline(model, paths, out_dir, nj, max_tokens, progress=lambda k: None, depth=2):
     """Three overlapped stages (the reference does them serially per file, infer_alns.py:97-117):
 
@@ -182,7 +185,7 @@ def run_pipeline(model, paths, out_dir, nj, max_tokens, progress=lambda k: None,
             idx, ids = load_alignment_idx(alnpath)
             n, L = idx.shape
             per_msa = max(1, n * (n - 1) // 2 * L)
-            step = max(1, int(max_tokens // per_msa))
+            step = max(1, min(MAX_BATCH, int(max_tokens // per_msa)))
             items = buckets.setdefault((n, L), [])
             items.append((alnpath, idx, ids))
             if len(items) >= step:
@@ -199,6 +202,7 @@ def run_pipeline(model, paths, out_dir, nj, max_tokens, progress=lambda k: None,
             retire(write_pool)
         for w in writes:
             progress(w.result())
+    model.check_device_error()    # a bounded device-side wait that timed out must not pass silently
 
 
 if __name__ == "__main__":

@@ -82,7 +82,7 @@ struct Plan {  // workspace carve-up for one (B, n, L, pair range)
   int n_chunks, ppc;        // k_col_partial (FFMA): pair chunks
   int n_chunks_tc, ppc_tc;  // k_col_partial_tc (tcgen05): pair chunks, ppc_tc a multiple of 32
   int n_chunks_ws, ppc_ws;  // k_col_partial_ws (tcgen05, warp specialised, one CTA per SM)
-  size_t off_x, off_part, off_colsum, off_colM, off_semb, off_qc, total;
+  size_t off_x, off_part, off_colsum, off_colM, off_semb, off_qc, off_head, total;
 };
 
 }  // namespace
@@ -109,6 +109,7 @@ struct pf_ctx {
   size_t peer_slot_floats = 0;
   unsigned peer_epoch = 0;
   int ws_prof = 0;              // env PF_WS_PROF=1: role timing into the dump buffer (test hook)
+  int head_impl = 1;            // 1: distance head fused into the last FFN launch (+ k_head_reduce), 0: k_head; env PF_HEAD_IMPL=fused|sep
   int* err_dev = nullptr;       // set by a kernel whose mbarrier wait timed out
   float* dump_dev = nullptr;    // test hook: raw accumulators of the first FFN tile
   // optional per-kernel timing (pf_profile_*)
@@ -192,6 +193,7 @@ Plan make_plan(const pf_ctx* h, int B, int n, int L, long long lo, long long hi)
   p.off_colM = off;    off = align_up(off + (size_t)B * L * PF_MROW * sizeof(float), 256);
   p.off_semb = off;    off = align_up(off + (size_t)B * n * L * PF_D * sizeof(float), 256);
   p.off_qc = off;      off = align_up(off + (size_t)B * p.Pl * L * 4 * sizeof(float), 256);   // per-token q~ of column attention
+  p.off_head = off;    off = align_up(off + (size_t)B * ((L + 3) / 4) * p.Pl * sizeof(float), 256);   // fused head: partial site sums
   p.total = off;
   return p;
 }
@@ -325,7 +327,10 @@ int pf_create(pf_handle* out, const pf_cfg* cfg, const float* const* weights_dev
       for (int hh = 0; hh < PF_H; ++hh) kc.wq[c][hh] = blk[b].col.wqk[4 + hh][c];
       kc.bo[c] = blk[b].col.bo[c];
       kc.b2[c] = blk[b].ffn.b2[c];
+      kc.whead[c] = head[0].whead[c];
     }
+    kc.bhead = head[0].bhead;
+    kc.pad[0] = kc.pad[1] = kc.pad[2] = 0.f;
     for (int hh = 0; hh < PF_H; ++hh) kc.bq[hh] = blk[b].col.bqk[4 + hh];
     h->ffn_const.push_back(kc);
   }
@@ -355,6 +360,7 @@ int pf_create(pf_handle* out, const pf_cfg* cfg, const float* const* weights_dev
   if (const char* e_impl = getenv("PF_FFN_IMPL")) h->ffn_impl = (strcmp(e_impl, "tc") == 0) ? 0 : 1;
   if (const char* e_row = getenv("PF_ROW_IMPL")) h->row_impl = (strcmp(e_row, "ld") == 0) ? 0 : (strcmp(e_row, "tma") == 0) ? 1 : 2;
   if (const char* e_prof = getenv("PF_WS_PROF")) h->ws_prof = atoi(e_prof);
+  if (const char* e_hd = getenv("PF_HEAD_IMPL")) h->head_impl = (strcmp(e_hd, "sep") == 0) ? 0 : 1;
   if (const char* e_col = getenv("PF_COL_IMPL")) h->col_impl = (strcmp(e_col, "cc") == 0) ? 0 : (strcmp(e_col, "tc1") == 0) ? 1 : 2;
   int rc = pf_ffn_tc_init();
   if (rc == 0) rc = pf_ffn_ws_init();
@@ -410,6 +416,7 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
   if (!h) return fail(PF_ERR_ARG, "pf_forward: null handle");
   if (!msa_idx_dev || !ws_dev) return fail(PF_ERR_ARG, "pf_forward: null buffer");
   if (B < 1 || n < 2 || L < 1) return fail(PF_ERR_ARG, "pf_forward: need B>=1, n>=2, L>=1 (got %d,%d,%d)", B, n, L);
+  if (B > 65535) return fail(PF_ERR_ARG, "pf_forward: B=%d exceeds 65535 alignments per call (the batch index is a launch-grid y/z dimension); split the batch", B);
   const long long P = (long long)n * (n - 1) / 2;
   if (pair_lo < 0 || pair_hi > P || pair_hi <= pair_lo)
     return fail(PF_ERR_ARG, "pf_forward: bad pair range [%lld,%lld) of %lld", (long long)pair_lo, (long long)pair_hi, P);
@@ -435,6 +442,8 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
   float* colM = (float*)(ws + pl.off_colM);
   float* semb = (float*)(ws + pl.off_semb);
   float* qcache = (float*)(ws + pl.off_qc);
+  float* headpart = (float*)(ws + pl.off_head);
+  bool head_fused = false;   // the last block's FFN launch emitted the head's partial sums (no k_head pass)
   const int rows = (int)(B * pl.Pl);
   const long long n_tok = (long long)rows * L;
   const int nb = h->cfg.nb_blocks;
@@ -481,7 +490,7 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
         k_row_attn_ws<<<rows < h->n_sm ? rows : h->n_sm, RW_THREADS, rw_smem_bytes(L), st>>>(x_tmap2, &bw->row, h->atc_dev + 2 * b, x,
                                                                                           rows, L, h->err_dev);
       else if (row_impl == 1)
-        k_row_attn_tma<<<rows, 256, row_smem + RT_STAGES * RT_STAGE_BYTES, st>>>(&bw->row, x, L);
+        k_row_attn_tma<<<rows, 256, row_smem + RT_STAGES * RT_STAGE_BYTES, st>>>(&bw->row, x, L, h->err_dev);
       else
         k_row_attn<0><<<rows, 256, row_smem, st>>>(&bw->row, h->head_dev, x, nullptr, nullptr, nullptr, n, L, pair_lo,
                                                    (int)pl.Pl, 0);
@@ -566,6 +575,9 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
     } else {
       Timed t_(h, PF_KC_FFN, st);
       const int prec = h->cfg.precision;
+      // last block, not a debug run, no accumulator dump / role timing requested: fuse the distance head
+      const bool fuse_head = (b == nb - 1) && !dbg && h->ffn_impl == 1 && h->head_impl == 1 && h->dump_dev == nullptr && !h->ws_prof;
+      head_fused = fuse_head;
       const int terms = prec == PF_PREC_BF16 ? 1 : prec == PF_PREC_FP16 ? 2 : 3;
       const int fmt = prec == PF_PREC_BF16 ? WS_FMT_BF16 : prec == PF_PREC_FP16 ? WS_FMT_F16 : WS_FMT_BF16X3;
       if (prec == PF_PREC_FP16 && h->ffn_impl != 1)
@@ -573,7 +585,8 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
       const int rc = h->ffn_impl == 1
                          ? pf_ffn_ws_launch(h->ffn_const[b], (prec == PF_PREC_FP16 ? h->tc16_dev : h->tc_dev) + b, x, colM,
                                             col_tc ? qcache : nullptr, L,
-                                            (int)pl.Pl, B, h->n_sm, fmt, terms, h->err_dev, h->dump_dev, h->ws_prof, st)
+                                            (int)pl.Pl, B, h->n_sm, fmt, terms, h->err_dev, h->dump_dev, h->ws_prof, st,
+                                            fuse_head ? headpart : nullptr)
                          : pf_ffn_tc_launch(&bw->col, h->tc_dev + b, x, colM, L, (int)pl.Pl, n_tok, h->n_sm, terms,
                                             h->err_dev, h->dump_dev, st);
       if (rc != 0) return fail(PF_ERR_CUDA, "pf_forward: tcgen05 FFN launch failed (%d)", rc);
@@ -583,7 +596,11 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
     stage = 3 * b + 3;
     if (dbg && stage == n_stages) return done();
   }
-  {
+  if (head_fused) {
+    Timed t_(h, PF_KC_HEAD, st);
+    dim3 g((unsigned)((pl.Pl + 255) / 256), B);
+    k_head_reduce<<<g, 256, 0, st>>>(headpart, (L + 3) / 4, (int)pl.Pl, L, dist_dev);
+  } else {
     Timed t_(h, PF_KC_HEAD, st);
     k_head<<<rows, 256, 0, st>>>(h->head_dev, x, L, dist_dev);
   }
@@ -729,19 +746,27 @@ long long pf_neighbor_joining(const float* dm_host, int n, const char* const* na
     snprintf(b, sizeof(b), "%.10f", x);
     return std::string(b);
   };
+  // Newick label: names holding blanks or Newick punctuation are single-quoted, embedded quotes doubled (nj.py: newick_label)
+  auto label = [](const char* s) {
+    std::string v(s);
+    if (!v.empty() && v.find_first_of(" \t\r\n,:;()[]'") == std::string::npos) return v;
+    std::string q = "'";
+    for (char c : v) { q += c; if (c == '\'') q += c; }
+    return q + "'";
+  };
   std::string tree;
   try {
   if (n == 1) {
-    tree = std::string(names[0]) + ";";
+    tree = label(names[0]) + ";";
   } else if (n == 2) {
     const double h = (double)dm_host[1] / 2;
-    tree = "(" + std::string(names[0]) + ":" + fmt(h) + "," + names[1] + ":" + fmt(h) + ");";
+    tree = "(" + label(names[0]) + ":" + fmt(h) + "," + label(names[1]) + ":" + fmt(h) + ");";
   } else {
     std::vector<double> d((size_t)n * n), r((size_t)n);
     for (size_t i = 0; i < (size_t)n * n; ++i) d[i] = (double)dm_host[i];
     std::vector<std::string> nodes((size_t)n);
     std::vector<int> active((size_t)n);
-    for (int i = 0; i < n; ++i) { nodes[i] = names[i]; active[i] = i; }
+    for (int i = 0; i < n; ++i) { nodes[i] = label(names[i]); active[i] = i; }
     auto D = [&](int i, int j) -> double& { return d[(size_t)i * n + j]; };
     while (active.size() > 3) {
       const int m = (int)active.size();
@@ -813,7 +838,7 @@ int pf_device_error(pf_handle h) {
   CUDA_TRY(cudaMemcpy(&v, h->err_dev, sizeof(int), cudaMemcpyDeviceToHost));
   if (v != 0) {
     cudaMemset(h->err_dev, 0, sizeof(int));
-    return fail(PF_ERR_CUDA, "a tensor-core pipeline barrier timed out on the device (flag %d)", v);
+    return fail(PF_ERR_CUDA, "a bounded device-side wait timed out (flag %d: 1/2 FFN pipeline, 3 peer exchange, 4-6 attention tile engine, 7 row staging ring); results of that call are invalid", v);
   }
   return PF_OK;
 }

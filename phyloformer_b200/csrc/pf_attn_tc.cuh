@@ -744,6 +744,17 @@ k_col_partial_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnTcW* __re
 #define RW_NS 3                                   // staging ring
 #define RW_NA 2                                   // operand image / k~ operand / D_qk ring
 #define RW_LAG 3
+// Order in which pass B walks the tiles of a row.  Reverse (last tile first): the tiles pass A staged last are
+// the ones most likely to be L2 hits when the re-read starts, so the part of the row that does fall out of L2 is
+// re-fetched once instead of pushing the still-unread part out ahead of the read pointer.
+#ifndef RW_B_REVERSE
+#define RW_B_REVERSE 1
+#endif
+#if RW_B_REVERSE
+#define RW_B_TILE(j, T) ((T) - 1 - (j))
+#else
+#define RW_B_TILE(j, T) (j)
+#endif
 #define RW_OFF_A1 0
 #define RW_OFF_XS (RW_NA * AT_A1_BYTES)
 #define RW_OFF_KT (RW_OFF_XS + RW_NS * 32768)
@@ -842,7 +853,7 @@ k_row_attn_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnW* __restric
     for (int i = 0; i <= m; ++i)
       for (int k = 0; k < T + lag; ++k) {
         if (i < m && k < T) load(i, k, pol_keep);
-        if (i >= 1 && k >= lag) load(i - 1, k - lag, pol_drop);
+        if (i >= 1 && k >= lag) load(i - 1, RW_B_TILE(k - lag, T), pol_drop);
       }
   } else if (warp < C2_NP1) {
     // =============================== P1: pass A (LN + split) and pass B (apply) ============
@@ -865,7 +876,7 @@ k_row_attn_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnW* __restric
         }
         if (i >= 1 && k >= lag) {        // ---- item B(i - 1, k - lag) ----
           {
-            const int st = nx % RW_NS, ib = i - 1, t = k - lag, par = ib & 1;
+            const int st = nx % RW_NS, ib = i - 1, t = RW_B_TILE(k - lag, T), par = ib & 1;
             ok = at_wait(BAR(RW_B_XFULL + st), (uint32_t)((nx / RW_NS) & 1), abortf) && ok;
             ok = at_wait(BAR(RW_B_FINDONE + par), (uint32_t)((ib >> 1) & 1), abortf) && ok;
             const float* fin = reinterpret_cast<const float*>(sm + RW_OFF_FIN + par * RW_FIN_BYTES);

@@ -35,6 +35,8 @@
 // Variants that were built, measured and removed again (DESIGN.md section 3.1 has the numbers):
 // final-row stores by the MMA warpgroup's idle warps, two producer threads per token row
 // (8 producer warps), epilogue warps above the producer in warp-id order.
+// 16 epilogue warps at <= 80 registers with a row-chunked producer (x2 staged through TMEM, 12 extra TMEM
+// instructions per row): built and measured in round 2, 34.7 vs 32.5 ms of FFN time per forward -> removed.
 #define WS_NCG (WS_EW / 4)            // epilogue column groups per TMEM lane quadrant
 #define WS_NPW 4                      // producer warps
 #define WS_PW0 WS_EW                  // first producer warp
@@ -68,6 +70,9 @@ struct PfFfnConst {
   float bo[PF_D];        // column out_proj bias
   float b2[PF_D];        // ffn.3 bias
   float bq[PF_H];        // folded q bias
+  float whead[PF_D];     // pwFNN.0.weight (HEAD instantiation: the last block's launch emits distances)
+  float bhead;
+  float pad[3];
 };
 
 typedef pf_u64 u64;  // packed fp32 pair helpers (pk2, up2, fma2, mul2, add2) live in pf_common.cuh
@@ -169,7 +174,11 @@ struct WsTileMap {  // tile index -> rows
 
 // QC: the column-attention q~ of every token comes from the cache written by k_col_partial_tc (16 B per
 // token, staged into the pad of the row slot) instead of being recomputed (LN_col + 4 dots of length 64).
-template <bool PROF, int FMT, bool QC>
+// HEAD: the launch of the last block does not write the activation back; the epilogue applies the distance head
+// (model.py:182-185: dot with pwFNN.0.weight, softplus) to the final row straight out of TMEM and writes one
+// partial site sum per (pair, 4-site window) into `dump` (there: headpart[b][window][pair]); k_head_reduce adds the
+// windows in a fixed order.  Saves the last 256 B/token write and k_head's 256 B/token read.
+template <bool PROF, int FMT, bool QC, bool HEAD = false>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restrict__ Wt, float* __restrict__ x,
                   const float* __restrict__ colM, const float* __restrict__ qcache, int L, int Pl, int B, int n_terms,
@@ -537,10 +546,29 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
       const int pair = pg * WS_G + g, site = w * WS_S + s;
       const bool valid = (pair < Pl) && (site < L);
       float* dst = x + (((size_t)b * Pl + (valid ? pair : 0)) * L + (valid ? site : 0)) * PF_D;
+      if (HEAD) {   // distance head on the final row (column group 0 takes the whole row); nothing is stored to x
+        static_assert(!HEAD || WS_S == 4, "the fused head sums a pair's sites with two lane shuffles");
+        if (chf == 0) {
+          float dot = kc.bhead;
+#pragma unroll
+          for (int jc = 0; jc < 4; ++jc) {
+            uint32_t v[16];
+            tmem_ld16(tmem + lane_base + WS_COL_D2 + 64 * a + 16 * jc, v);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+            dot = fmaf(__uint_as_float(v[i]), kc.whead[16 * jc + i], dot);
+          }
+          float sp = valid ? softplus20(dot) : 0.f;
+          sp += __shfl_xor_sync(PF_FULL, sp, 1);      // the tile's WS_S = 4 sites of a pair sit in adjacent lanes
+          sp += __shfl_xor_sync(PF_FULL, sp, 2);
+          if ((lane & 3) == 0 && pair < Pl) dump[((size_t)b * tm.nW + w) * Pl + pair] = sp;
+        }
+      }
       // D2 has four 16-column chunks; chunk j goes to column group (WS_NCG-1-j) mod WS_NCG, which
       // gives the extra store chunk to the group with the fewest GELU chunks
 #pragma unroll
-      for (int jc = 0; jc < 4; ++jc) {
+      for (int jc = 0; jc < (HEAD ? 0 : 4); ++jc) {
         if ((WS_NCG - 1 - jc % WS_NCG) == chf) {
           uint32_t v[16];
           tmem_ld16(tmem + lane_base + WS_COL_D2 + 64 * a + 16 * jc, v);
@@ -601,6 +629,9 @@ inline int pf_ffn_ws_init_qc() {
   if (rc == 0) rc = (int)cudaFuncSetAttribute(k_colapply_ffn_ws<true, WS_FMT_BF16X3, QC>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
   if (rc == 0) rc = (int)cudaFuncSetAttribute(k_colapply_ffn_ws<false, WS_FMT_BF16, QC>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
   if (rc == 0) rc = (int)cudaFuncSetAttribute(k_colapply_ffn_ws<false, WS_FMT_F16, QC>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
+  if (rc == 0) rc = (int)cudaFuncSetAttribute(k_colapply_ffn_ws<false, WS_FMT_BF16X3, QC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
+  if (rc == 0) rc = (int)cudaFuncSetAttribute(k_colapply_ffn_ws<false, WS_FMT_BF16, QC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
+  if (rc == 0) rc = (int)cudaFuncSetAttribute(k_colapply_ffn_ws<false, WS_FMT_F16, QC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
   return rc;
 }
 inline int pf_ffn_ws_init() {
@@ -611,6 +642,17 @@ inline int pf_ffn_ws_init() {
 // fmt: WS_FMT_*; n_terms: MMA passes per product (3 for BF16X3, 1 for BF16, 2 for F16 = hi and lo weights).
 // Wt must hold the weight images of the matching 16-bit format.  qcache: the per-token q~ cache of
 // k_col_partial_tc, or nullptr (the producer then recomputes q~ itself).
+template <bool QC>
+inline int pf_ffn_ws_launch_head(const PfFfnConst& kc, const PfFfnTcW* Wt, float* x, const float* colM, const float* qcache,
+                                 int L, int Pl, int B, int grid, int fmt, int n_terms, int* err_flag, float* headpart, cudaStream_t st) {
+  if (fmt == WS_FMT_F16)
+    k_colapply_ffn_ws<false, WS_FMT_F16, QC, true><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(kc, Wt, x, colM, qcache, L, Pl, B, n_terms, err_flag, headpart);
+  else if (fmt == WS_FMT_BF16)
+    k_colapply_ffn_ws<false, WS_FMT_BF16, QC, true><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(kc, Wt, x, colM, qcache, L, Pl, B, n_terms, err_flag, headpart);
+  else
+    k_colapply_ffn_ws<false, WS_FMT_BF16X3, QC, true><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(kc, Wt, x, colM, qcache, L, Pl, B, n_terms, err_flag, headpart);
+  return (int)cudaGetLastError();
+}
 template <bool QC>
 inline int pf_ffn_ws_launch_qc(const PfFfnConst& kc, const PfFfnTcW* Wt, float* x, const float* colM, const float* qcache,
                                int L, int Pl, int B, int grid, int fmt, int n_terms, int* err_flag, float* dump, int prof,
@@ -626,11 +668,15 @@ inline int pf_ffn_ws_launch_qc(const PfFfnConst& kc, const PfFfnTcW* Wt, float* 
   return (int)cudaGetLastError();
 }
 inline int pf_ffn_ws_launch(const PfFfnConst& kc, const PfFfnTcW* Wt, float* x, const float* colM, const float* qcache, int L,
-                            int Pl, int B, int n_sm, int fmt, int n_terms, int* err_flag, float* dump, int prof, cudaStream_t st) {
+                            int Pl, int B, int n_sm, int fmt, int n_terms, int* err_flag, float* dump, int prof, cudaStream_t st,
+                            float* headpart = nullptr) {
   const long long nt = (long long)B * ((L + WS_S - 1) / WS_S) * ((Pl + WS_G - 1) / WS_G);
   if (nt > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
   if (fmt != WS_FMT_BF16X3 && n_terms > 2) return (int)cudaErrorInvalidValue;   // no lo activations in these formats
   const int grid = (int)(nt < n_sm ? nt : n_sm);
+  if (headpart != nullptr)
+    return qcache != nullptr ? pf_ffn_ws_launch_head<true>(kc, Wt, x, colM, qcache, L, Pl, B, grid, fmt, n_terms, err_flag, headpart, st)
+                             : pf_ffn_ws_launch_head<false>(kc, Wt, x, colM, qcache, L, Pl, B, grid, fmt, n_terms, err_flag, headpart, st);
   return qcache != nullptr
              ? pf_ffn_ws_launch_qc<true>(kc, Wt, x, colM, qcache, L, Pl, B, grid, fmt, n_terms, err_flag, dump, prof, st)
              : pf_ffn_ws_launch_qc<false>(kc, Wt, x, colM, qcache, L, Pl, B, grid, fmt, n_terms, err_flag, dump, prof, st);

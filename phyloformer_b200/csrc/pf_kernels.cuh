@@ -299,9 +299,11 @@ __device__ __forceinline__ void rt_issue(uint32_t dst, const float* src, uint32_
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void rt_wait(uint32_t bar, uint32_t parity) {
+// Bounded wait (never hangs the GPU).  On a timeout the device error flag is raised (pf_device_error reports it)
+// instead of silently consuming a stage that never arrived.
+__device__ __forceinline__ void rt_wait(uint32_t bar, uint32_t parity, int* err_flag) {
   uint32_t ok = 0;
-  for (uint32_t spin = 0; !ok && spin < (1u << 22); ++spin) {  // bounded: never hang the GPU
+  for (uint32_t spin = 0; !ok && spin < (1u << 22); ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 1000;\n\t"
@@ -310,10 +312,11 @@ __device__ __forceinline__ void rt_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
   }
+  if (!ok && err_flag != nullptr) *err_flag = 7;
 }
 
 __global__ void __launch_bounds__(256, 2)
-k_row_attn_tma(const PfAttnW* __restrict__ W, float* __restrict__ x, int L) {
+k_row_attn_tma(const PfAttnW* __restrict__ W, float* __restrict__ x, int L, int* __restrict__ err_flag) {
   extern __shared__ __align__(128) unsigned char smem_rt[];
   unsigned char* ring = smem_rt;                                               // RT_STAGES x 16 KB
   RowSmem& sm = *reinterpret_cast<RowSmem*>(smem_rt + RT_STAGES * RT_STAGE_BYTES);
@@ -364,7 +367,7 @@ k_row_attn_tma(const PfAttnW* __restrict__ W, float* __restrict__ x, int L) {
   float own = 0.f;
   for (int c = 0; c < n_chunks; ++c) {
     const int st = c % RT_STAGES;
-    rt_wait(bar_u32 + 8 * st, (uint32_t)((c / RT_STAGES) & 1));
+    rt_wait(bar_u32 + 8 * st, (uint32_t)((c / RT_STAGES) & 1), err_flag);
     const float* stage = reinterpret_cast<const float*>(ring + st * RT_STAGE_BYTES);
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -444,7 +447,7 @@ k_row_attn_tma(const PfAttnW* __restrict__ W, float* __restrict__ x, int L) {
   const float4 qi = *reinterpret_cast<const float4*>(sm.qinv);
   for (int c = n_chunks; c < 2 * n_chunks; ++c) {
     const int st = resident ? (c - n_chunks) : (c % RT_STAGES);
-    if (!resident) rt_wait(bar_u32 + 8 * st, (uint32_t)((c / RT_STAGES) & 1));
+    if (!resident) rt_wait(bar_u32 + 8 * st, (uint32_t)((c / RT_STAGES) & 1), err_flag);
     const float* stage = reinterpret_cast<const float*>(ring + st * RT_STAGE_BYTES);
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -892,6 +895,17 @@ k_head(const PfHeadW* __restrict__ hw, const float* __restrict__ x, int L, float
     for (int i = 0; i < 32; ++i) s += red[i];
     dist[blockIdx.x] = s / (float)L;
   }
+}
+
+// Fused head, step 2: dist[b,p] = (sum over the 4-site windows of the partial softplus sums) / L, fixed order.
+// headpart[b][w][p] is written by the HEAD instantiation of k_colapply_ffn_ws.
+__global__ void k_head_reduce(const float* __restrict__ headpart, int nW, int Pl, int L, float* __restrict__ dist) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (p >= Pl) return;
+  const float* src = headpart + (size_t)b * nW * Pl + p;
+  float s = 0.f;
+  for (int w = 0; w < nW; ++w) s += src[(size_t)w * Pl];
+  dist[(size_t)b * Pl + p] = s / (float)L;
 }
 
 // (B,P) upper-triangle vectors -> (B,n,n) symmetric matrices        infer_alns.py:14-25

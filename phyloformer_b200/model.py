@@ -99,6 +99,7 @@ class Phyloformer(nn.Module):
 
         self._handle = None
         self._handle_key = None
+        self._handle_gen = 0  # bumped whenever the native handle is created or destroyed (graphed runners check it)
         self._ws = None
         self._shard = None  # (group, rank, world)
         self._exchange = "auto"
@@ -133,6 +134,7 @@ class Phyloformer(nn.Module):
         with torch.cuda.device(device):
             _cabi.check(lib.pf_create(ctypes.byref(handle), ctypes.byref(cfg), ptrs, len(tensors)), "pf_create")
         self._handle, self._handle_key = handle, key
+        self._handle_gen += 1
         return lib
 
     def _release(self):
@@ -140,6 +142,7 @@ class Phyloformer(nn.Module):
             _cabi.load().pf_destroy(self._handle)
             self._handle = None
             self._handle_key = None
+            self._handle_gen += 1
 
     def __del__(self):
         try:
@@ -173,7 +176,7 @@ class Phyloformer(nn.Module):
         world = dist.get_world_size(group)
         self._shard = (group, dist.get_rank(group), world) if world > 1 else None
         self._exchange = exchange
-        self._peer = None          # (symmetric tensor, handle, slot_floats)
+        self._peer = None          # (symmetric tensor, handle, slot_floats, handle generation it is bound to)
         self._peer_failed = False
         return self
 
@@ -191,6 +194,11 @@ class Phyloformer(nn.Module):
         if self._exchange == "auto" and dist.get_backend(group) != "nccl":
             return False
         if self._peer is not None and self._peer[2] >= need_floats:
+            if self._peer[3] != self._handle_gen:   # the handle was re-created (weights changed): bind the same buffers again
+                buf, hdl, slot, _ = self._peer
+                ptrs = (ctypes.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
+                _cabi.check(lib.pf_set_peer_exchange(self._handle, rank, world, ptrs, slot), "pf_set_peer_exchange")
+                self._peer = (buf, hdl, slot, self._handle_gen)
             return True
         try:
             import torch.distributed._symmetric_memory as symm_mem
@@ -203,7 +211,7 @@ class Phyloformer(nn.Module):
             dist.barrier(group)           # every rank has zeroed its flags before anyone publishes
             ptrs = (ctypes.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
             _cabi.check(lib.pf_set_peer_exchange(self._handle, rank, world, ptrs, slot), "pf_set_peer_exchange")
-            self._peer = (buf, hdl, slot)
+            self._peer = (buf, hdl, slot, self._handle_gen)
             return True
         except Exception as e:  # noqa: BLE001
             if self._exchange == "p2p":
@@ -347,20 +355,36 @@ class Phyloformer(nn.Module):
         if ex.dtype != torch.uint8 or not ex.is_cuda:
             raise TypeError("make_graphed expects a CUDA uint8 tensor of residue codes")
         static_in = ex.contiguous().clone()
-        self.forward_idx(static_in, squeeze=False)          # warm-up: handle, workspace, lazy init
+        self.forward_idx(static_in, squeeze=False)          # warm-up: handle, lazy init
         torch.cuda.synchronize(static_in.device)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            static_out = self.forward_idx(static_in, squeeze=False)
+        # The graph bakes in raw pointers to the workspace and to the handle's device buffers.  It therefore gets
+        # a workspace of its own (held by the closure; eager calls keep using / regrowing self._ws) and remembers
+        # the handle generation and precision it was captured with: a weight change, .to() or set_precision()
+        # afterwards makes run() raise instead of replaying against freed memory.
+        B, n, L = static_in.shape
+        lib = _cabi.load()
+        nbytes = lib.pf_workspace_bytes(self._handle, B, n, L, 0, sharding.n_pairs(n))
+        private_ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=static_in.device)
+        eager_ws, self._ws = self._ws, private_ws
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self.forward_idx(static_in, squeeze=False)
+        finally:
+            self._ws = eager_ws
+        gen, prec = self._handle_gen, self.precision
 
         def run(idx: torch.Tensor) -> torch.Tensor:
             idx = idx[None] if idx.dim() == 2 else idx
             if idx.shape != static_in.shape or idx.dtype != torch.uint8:
                 raise ValueError(f"graphed forward expects uint8 {tuple(static_in.shape)}, got {idx.dtype} {tuple(idx.shape)}")
+            if self._handle_gen != gen or self.precision != prec or self._handle_key != (static_in.device, self._weights_key()):
+                raise RuntimeError("the model changed (weights, device or precision) after make_graphed(): capture again")
             static_in.copy_(idx, non_blocking=True)
             graph.replay()
             return static_out
 
+        run.workspace = private_ws  # owned by the runner
         run.graph = graph  # keep alive / introspection
         return run
 

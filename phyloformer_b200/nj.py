@@ -9,8 +9,22 @@ from typing import List, Sequence
 import numpy as np
 
 
+_NEWICK_RESERVED = set(" \t\r\n,:;()[]'")
+
+
+def newick_label(name) -> str:
+    """A taxon name as a Newick label: FASTA ids are whole header lines (reference data.py:22), so they can hold
+    blanks or Newick punctuation; such names are single-quoted with embedded quotes doubled (as the skbio
+    writer behind the reference's `--trees` does), all others are written as they are."""
+    name = str(name)
+    if name == "" or any(c in _NEWICK_RESERVED for c in name):
+        return "'" + name.replace("'", "''") + "'"
+    return name
+
+
 def neighbor_joining(dm: np.ndarray, ids: Sequence[str], clip_negative: bool = True) -> str:
     d = np.array(dm, dtype=np.float64)
+    ids = [newick_label(i) for i in ids]
     n = d.shape[0]
     if d.shape != (n, n) or n != len(ids):
         raise ValueError("distance matrix and ids do not match")

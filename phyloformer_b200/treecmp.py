@@ -34,10 +34,29 @@ def parse_newick(text: str) -> _Node:
                     pos += 1
                     break
                 raise ValueError(f"bad newick at {pos}: {s[pos:pos + 20]!r}")
-        start = pos
-        while pos < len(s) and s[pos] not in ",():;":
+        while pos < len(s) and s[pos] in " \t\n":
             pos += 1
-        label = s[start:pos].strip()
+        if pos < len(s) and s[pos] == "'":           # quoted label: '' is an embedded quote
+            pos += 1
+            chars = []
+            while True:
+                if pos >= len(s):
+                    raise ValueError("unterminated quoted label")
+                if s[pos] == "'":
+                    if pos + 1 < len(s) and s[pos + 1] == "'":
+                        chars.append("'")
+                        pos += 2
+                        continue
+                    pos += 1
+                    break
+                chars.append(s[pos])
+                pos += 1
+            label = "".join(chars)
+        else:
+            start = pos
+            while pos < len(s) and s[pos] not in ",():;":
+                pos += 1
+            label = s[start:pos].strip()
         if label and not node.children:
             node.name = label
         if pos < len(s) and s[pos] == ":":

@@ -2,6 +2,8 @@
 import json
 import os
 
+import numpy as np
+
 from phyloformer_b200.treecmp import bipartitions, rf_distance
 from tests._util import GOLDEN
 
@@ -61,3 +63,50 @@ def test_c_neighbor_joining_matches_python():
         assert na == nb and np.abs(pa - pb).max() < 1e-8
     assert neighbor_joining_c(np.array([[0, 2.0], [2.0, 0]]), ["a", "b"]) == "(a:1.0000000000,b:1.0000000000);"
     assert neighbor_joining_c(np.zeros((1, 1)), ["solo"]) == "solo;"
+
+
+def test_neighbor_joining_known_answer():
+    """External known answer: the five-taxon matrix of the neighbour-joining worked example (Saitou & Nei's
+    algorithm as in the Wikipedia article; the same matrix is the doctest of `skbio.tree.nj`, the call behind the
+    reference's `--trees`, infer_alns.py:120-123), whose published result is
+        (d:2, (c:4, (b:3, a:2):3):2, e:1);
+    including both Q-matrix ties (a,b)/(d,e) and (u,c)/(d,e), which must resolve to the first pair."""
+    from phyloformer_b200.nj import neighbor_joining, neighbor_joining_c
+    from phyloformer_b200.treecmp import parse_newick
+    dm = np.array([[0, 5, 9, 9, 8], [5, 0, 10, 10, 9], [9, 10, 0, 8, 7], [9, 10, 8, 0, 3], [8, 9, 7, 3, 0]], dtype=np.float64)
+    want = "(((a:2.0000000000,b:3.0000000000):3.0000000000,c:4.0000000000):2.0000000000,d:2.0000000000,e:1.0000000000);"
+    for fn in (neighbor_joining, neighbor_joining_c):
+        nwk = fn(dm, list("abcde"))
+        assert nwk == want, (fn.__name__, nwk)
+        splits, leaves = bipartitions(nwk)
+        assert leaves == set("abcde") and splits == {frozenset("cde"), frozenset("de")}
+        # leaf branch lengths of the published tree
+        root = parse_newick(nwk)
+        got = {}
+
+        def walk(nd):
+            if nd.name is not None:
+                got[nd.name] = nd.length
+            for ch in nd.children:
+                walk(ch)
+        walk(root)
+        assert got == {"a": 2.0, "b": 3.0, "c": 4.0, "d": 2.0, "e": 1.0}
+    s1, _ = bipartitions(want)
+    s2, _ = bipartitions("(d:2.0,(c:4.0,(b:3.0,a:2.0):3.0):2.0,e:1.0);")        # the published Newick
+    assert s1 == s2 and len(s1) == 2
+
+
+def test_newick_labels_with_reserved_characters_are_quoted():
+    """FASTA ids are whole header lines: blanks and Newick punctuation must not break the tree file."""
+    from phyloformer_b200.nj import neighbor_joining, neighbor_joining_c, newick_label
+    assert newick_label("plain_id.1|x") == "plain_id.1|x"
+    assert newick_label("Homo sapiens (human)") == "'Homo sapiens (human)'"
+    assert newick_label("it's") == "'it''s'"
+    ids = ["sp A", "b:1", "c,d", "(e)", "f'g", "ok"]
+    rng = np.random.default_rng(3)
+    dm = rng.uniform(0.1, 1.0, (6, 6)); dm = dm + dm.T; np.fill_diagonal(dm, 0)
+    for fn in (neighbor_joining, neighbor_joining_c):
+        nwk = fn(dm, ids)
+        _, leaves = bipartitions(nwk)
+        assert leaves == set(ids), (fn.__name__, nwk)
+    assert neighbor_joining_c(np.array([[0, 2.0], [2.0, 0]]), ["a b", "c"]) == "('a b':1.0000000000,c:1.0000000000);"

@@ -23,6 +23,10 @@ for step in "$@"; do
                timeout 600 python tools/diag_variants.py one ${DIAG_SHAPE:-100 500 1} tc tma > $out/coredump_run.txt 2>&1 );
              for c in /tmp/pf_core_*; do [ -f "$c" ] && timeout 300 cuda-gdb -batch -ex "target cudacore $c" -ex "info cuda kernels" -ex "info cuda lanes" -ex "bt" -ex "x/6i \$pc" > $out/coredump_gdb.txt 2>&1 && break; done ;;
     gdbrun)  timeout 900 cuda-gdb -batch -ex run -ex "info cuda kernels" -ex bt -ex "x/6i \$pc" --args python tools/diag_variants.py one ${DIAG_SHAPE:-100 500 1} tc tma > $out/gdbrun.txt 2>&1 ;;
+    head)    timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "fused_head or stage_taps or synthetic_shapes or tcgen05_ffn or forward_idx_equals" -s > $out/pytest_head.txt 2>&1; echo "rc=$?" >> $out/pytest_head.txt ;;
+    lean)    PF_LIB=build/libpf_lean.so timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "fused_head or stage_taps or synthetic_shapes or forward_idx_equals" -s > $out/pytest_lean.txt 2>&1; echo "rc=$?" >> $out/pytest_lean.txt ;;
+    ab)      tools/ab_bench.sh ${AB_REPS:-2} phyloformer_b200/libpf_sm100.so $AB_LIBS > $out/ab.txt 2>&1 ;;
+    quick)   timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "tensor_core_attention or fused_head or stage_taps or cuda_graph or cli_end or reference_cases" -s > $out/pytest_quick.txt 2>&1; echo "rc=$?" >> $out/pytest_quick.txt ;;
     smoke)   timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke.txt 2>&1; echo "rc=$?" >> $out/smoke.txt ;;
     *) echo "unknown step $step" ;;
   esac
