@@ -424,9 +424,20 @@ def run_native(args):
                     "frac": tf / peak, "traffic": None, "achieved_issued": tf * issued, "frac_issued": tf * issued / peak,
                     "hbm_gbs": local_tokens * BYTES_PER_TOKEN_FFN / (ffn_avg * 1e-3) / 1e9,
                     "note": f"useful FLOPs = 65536/token; {int(issued)} 16-bit MMA passes issued per product"}
+    # the streaming kernels against the HBM roofline: algorithmic bytes per launch / live launch time
+    nb = 6
+    hbm_alg = {"row": local_tokens * (512.0 * (nb - 1) + 256.0) / nb,   # read + write in place; block 0 only writes (x0 comes from the MSA)
+               "colsum": local_tokens * 256.0,                          # one read pass
+               "ffn": local_tokens * (512.0 * nb - (256.0 if prof.get("head", (0, 0))[0] < 0.2 * args.steps else 0.0)) / nb}
+    for k, alg in hbm_alg.items():
+        if k in kernels and kernels[k]["launches_per_step"] > 0:
+            per_launch_ms = kernels[k]["ms_per_step"] / kernels[k]["launches_per_step"]
+            gbs = alg / (per_launch_ms * 1e-3) / 1e9
+            kernels[k].update({"avg_launch_ms": per_launch_ms, "algorithmic_bytes_per_launch": alg, "hbm_gbs": gbs,
+                               "hbm_frac": gbs / peaks["hbm_gbs"]})
     # DRAM traffic of the dominant kernel from the committed ncu capture (same workload, 1 GPU)
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         if tr["workload"] == args.workload and world == tr["n_gpus"] and args.precision != "fp32":
             roofline["traffic"] = tr["dram_bytes_per_launch"]["k_colapply_ffn_ws"]
             roofline["traffic_algorithmic"] = tr["algorithmic_bytes_per_launch"]["k_colapply_ffn_ws"]

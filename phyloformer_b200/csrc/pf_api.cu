@@ -109,6 +109,9 @@ struct pf_ctx {
   size_t peer_slot_floats = 0;
   unsigned peer_epoch = 0;
   int ws_prof = 0;              // env PF_WS_PROF=1: role timing into the dump buffer (test hook)
+  Row0Tab* row0_dev = nullptr;  // residue-pair tables of block 0's row attention (k_row_attn_combo)
+  int row0_impl = 1;            // 1: k_row_attn_combo for residue-code inputs, 0: k_row_attn<1> always; env PF_ROW0_IMPL=combo|ffma
+  int exch_impl = 1;            // 1: k_col_exchange (one fused, site-chunked launch per block), 0: reduce / sync / finalize launches; env PF_EXCH_IMPL=fused|split
   int head_impl = 1;            // 1: distance head fused into the last FFN launch (+ k_head_reduce), 0: k_head; env PF_HEAD_IMPL=fused|sep
   int* err_dev = nullptr;       // set by a kernel whose mbarrier wait timed out
   float* dump_dev = nullptr;    // test hook: raw accumulators of the first FFN tile
@@ -334,6 +337,25 @@ int pf_create(pf_handle* out, const pf_cfg* cfg, const float* const* weights_dev
     for (int hh = 0; hh < PF_H; ++hh) kc.bq[hh] = blk[b].col.bqk[4 + hh];
     h->ffn_const.push_back(kc);
   }
+  // Residue-pair tables for block 0's row attention (k_row_attn_combo): LN(x0), k~ and q~ of the 22 x 22 possible
+  // pair embeddings x0 = T[a] + T[b] (fp32 sum as on the device, everything after it in fp64)
+  std::vector<Row0Tab> row0(1);
+  for (int a = 0; a < PF_NCHAR; ++a)
+    for (int bb = 0; bb < PF_NCHAR; ++bb) {
+      const int c = a * PF_NCHAR + bb;
+      double x0[PF_D], mean = 0.0, var = 0.0;
+      for (int k = 0; k < PF_D; ++k) { x0[k] = (double)(head[0].table[a][k] + head[0].table[bb][k]); mean += x0[k]; }
+      mean /= PF_D;
+      for (int k = 0; k < PF_D; ++k) var += (x0[k] - mean) * (x0[k] - mean);
+      const double rstd = 1.0 / sqrt(var / PF_D + 1e-5);
+      double nn[PF_D];
+      for (int k = 0; k < PF_D; ++k) { nn[k] = (x0[k] - mean) * rstd; row0[0].n[c][k] = (float)nn[k]; }
+      for (int v = 0; v < 8; ++v) {
+        double z = blk[0].row.bqk[v];
+        for (int k = 0; k < PF_D; ++k) z += (double)blk[0].row.wqk[v][k] * nn[k];
+        row0[0].kq[c][v] = (float)(z > 0.0 ? z + 1.0 : exp(z));
+      }
+    }
   auto cleanup = [&]() { pf_destroy(h); };
   cudaError_t e;
   if ((e = cudaMalloc(&h->head_dev, sizeof(PfHeadW))) != cudaSuccess ||
@@ -342,6 +364,8 @@ int pf_create(pf_handle* out, const pf_cfg* cfg, const float* const* weights_dev
       (e = cudaMalloc(&h->tc16_dev, sizeof(PfFfnTcW) * nb)) != cudaSuccess ||
       (e = cudaMalloc(&h->atc_dev, sizeof(PfAttnTcW) * 2 * nb)) != cudaSuccess ||
       (e = cudaMemcpy(h->atc_dev, atc.data(), sizeof(PfAttnTcW) * 2 * nb, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMalloc(&h->row0_dev, sizeof(Row0Tab))) != cudaSuccess ||
+      (e = cudaMemcpy(h->row0_dev, row0.data(), sizeof(Row0Tab), cudaMemcpyHostToDevice)) != cudaSuccess ||
       (e = cudaMalloc(&h->err_dev, sizeof(int))) != cudaSuccess ||
       (e = cudaMemset(h->err_dev, 0, sizeof(int))) != cudaSuccess ||
       (e = cudaMemcpy(h->head_dev, head.data(), sizeof(PfHeadW), cudaMemcpyHostToDevice)) != cudaSuccess ||
@@ -357,9 +381,12 @@ int pf_create(pf_handle* out, const pf_cfg* cfg, const float* const* weights_dev
   CUDA_TRY(cudaFuncSetAttribute(k_row_attn<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_TRY(cudaFuncSetAttribute(k_row_attn<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_TRY(cudaFuncSetAttribute(k_row_attn_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(k_row_attn_combo, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  if (const char* e_r0 = getenv("PF_ROW0_IMPL")) h->row0_impl = (strcmp(e_r0, "ffma") == 0) ? 0 : 1;
   if (const char* e_impl = getenv("PF_FFN_IMPL")) h->ffn_impl = (strcmp(e_impl, "tc") == 0) ? 0 : 1;
   if (const char* e_row = getenv("PF_ROW_IMPL")) h->row_impl = (strcmp(e_row, "ld") == 0) ? 0 : (strcmp(e_row, "tma") == 0) ? 1 : 2;
   if (const char* e_prof = getenv("PF_WS_PROF")) h->ws_prof = atoi(e_prof);
+  if (const char* e_ex = getenv("PF_EXCH_IMPL")) h->exch_impl = (strcmp(e_ex, "split") == 0) ? 0 : 1;
   if (const char* e_hd = getenv("PF_HEAD_IMPL")) h->head_impl = (strcmp(e_hd, "sep") == 0) ? 0 : 1;
   if (const char* e_col = getenv("PF_COL_IMPL")) h->col_impl = (strcmp(e_col, "cc") == 0) ? 0 : (strcmp(e_col, "tc1") == 0) ? 1 : 2;
   int rc = pf_ffn_tc_init();
@@ -378,6 +405,7 @@ void pf_destroy(pf_handle h) {
   if (h->tc16_dev) cudaFree(h->tc16_dev);
   if (h->atc_dev) cudaFree(h->atc_dev);
   if (h->err_dev) cudaFree(h->err_dev);
+  if (h->row0_dev) cudaFree(h->row0_dev);
   if (h->peers_dev) cudaFree(h->peers_dev);
   for (auto& r : h->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : h->pool) cudaEventDestroy(e);
@@ -477,10 +505,18 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
     // ---- row attention (block 0: fused with the pair embedding) ----
     if (b == 0) {
       const int embed_only = (dbg && n_stages == 0) ? 1 : 0;
-      {
+      // residue codes (forward_idx, or forward(x) whose x turned out one-hot: device flag): tables + gather;
+      // soft inputs: the FFMA kernel.  Both check the flag on the device; the one that does not apply exits at once.
+      const bool combo = h->row0_impl == 1 && !embed_only && row0_smem_bytes(L) <= 200 * 1024;
+      if (combo) {
+        Timed t_(h, PF_KC_ROW, st);
+        k_row_attn_combo<<<rows, 256, row0_smem_bytes(L), st>>>(&bw->row, h->head_dev, h->row0_dev, x, msa_idx_dev, flag, n, L,
+                                                               pair_lo, (int)pl.Pl);
+      }
+      if (!combo || flag != nullptr) {
         Timed t_(h, PF_KC_ROW, st);
         k_row_attn<1><<<rows, 256, row_smem, st>>>(&bw->row, h->head_dev, x, msa_idx_dev, semb, flag, n, L, pair_lo,
-                                                   (int)pl.Pl, embed_only);
+                                                   (int)pl.Pl, combo ? 2 : embed_only);
       }
       CUDA_TRY(cudaGetLastError());
       if (embed_only) return done();
@@ -527,6 +563,9 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
       const int spc = std::max(1, std::min(PF_FS, n_sites / (2 * h->n_sm)));
       const unsigned gfs = (unsigned)((n_sites + spc - 1) / spc);
       const bool peer = (h->peer_world > 1) && ((pair_hi - pair_lo) != P);
+      // fused form: at most PF_PEER_MAX_CTAS - 1 CTAs (the flag table has one word per rank and CTA; the last column
+      // belongs to the three-launch form), each looping over its site groups; the same grid on every rank
+      const unsigned gex = std::min(gfs, (unsigned)std::min(PF_PEER_MAX_CTAS - 1, 2 * h->n_sm));
       if (peer) {
         const size_t need = (size_t)B * L * PF_COLSUM;
         if (need > h->peer_slot_floats)
@@ -534,19 +573,30 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
         const unsigned epoch = ++h->peer_epoch;
         const int slot = (int)(epoch & 1u);
         float* my_slot = reinterpret_cast<float*>(h->peer_self + PF_PEER_FLAG_BYTES) + (size_t)slot * h->peer_slot_floats;
-        {
+        if (h->exch_impl == 1) {
           Timed t_(h, PF_KC_COLFIN, st);
-          k_col_reduce<<<gfs, 256, 0, st>>>(&bw->col, part, n_part, n_sites, spc, my_slot);
+          k_col_exchange<<<gex, 256, 0, st>>>(&bw->col, part, n_part, n_sites, spc, my_slot, h->peers_dev, h->peer_rank,
+                                              h->peer_world, slot, h->peer_slot_floats, epoch, (float)P, colM, h->err_dev);
+        } else {
+          {
+            Timed t_(h, PF_KC_COLFIN, st);
+            k_col_reduce<<<gfs, 256, 0, st>>>(&bw->col, part, n_part, n_sites, spc, my_slot);
+          }
+          {
+            Timed t_(h, PF_KC_COLFIN, st);
+            k_peer_sync<<<1, 32, 0, st>>>(h->peers_dev, h->peer_rank, h->peer_world, epoch, h->err_dev);
+          }
+          {
+            Timed t_(h, PF_KC_COLFIN, st);
+            k_col_finalize_peer<<<gfs, 256, 0, st>>>(&bw->col, h->peers_dev, h->peer_world, slot, h->peer_slot_floats,
+                                                     (float)P, n_sites, spc, colM);
+          }
         }
-        {
-          Timed t_(h, PF_KC_COLFIN, st);
-          k_peer_sync<<<1, 32, 0, st>>>(h->peers_dev, h->peer_rank, h->peer_world, epoch, h->err_dev);
-        }
-        {
-          Timed t_(h, PF_KC_COLFIN, st);
-          k_col_finalize_peer<<<gfs, 256, 0, st>>>(&bw->col, h->peers_dev, h->peer_world, slot, h->peer_slot_floats,
-                                                   (float)P, n_sites, spc, colM);
-        }
+        CUDA_TRY(cudaGetLastError());
+      } else if (!reduce && h->exch_impl == 1) {   // one rank holds every pair: same kernel, no flags, no peers, one site group per CTA
+        Timed t_(h, PF_KC_COLFIN, st);
+        k_col_exchange<<<gfs, 256, 0, st>>>(&bw->col, part, n_part, n_sites, spc, colsum, nullptr, 0, 1, 0, 0, 0u, (float)P,
+                                            colM, h->err_dev);
         CUDA_TRY(cudaGetLastError());
       } else {
         {

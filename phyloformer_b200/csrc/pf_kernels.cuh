@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(256, 2)
 k_row_attn(const PfAttnW* __restrict__ W, const PfHeadW* __restrict__ hw, float* __restrict__ x,
            const uint8_t* __restrict__ msa, const float* __restrict__ semb,
            const int* __restrict__ soft_flag, int n, int L, long long pair_lo, int Pl, int embed_only) {
+  if (MODE == 1 && embed_only == 2 && (soft_flag == nullptr || *soft_flag == 0)) return;   // residue codes: k_row_attn_combo did this row
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RowSmem& sm = *reinterpret_cast<RowSmem*>(smem_raw);
   float* qcache = reinterpret_cast<float*>(smem_raw + sizeof(RowSmem));  // [L][4]
@@ -275,9 +276,179 @@ k_row_attn(const PfAttnW* __restrict__ W, const PfHeadW* __restrict__ hw, float*
       a = fmaf(Mr[i].y, q.y, a);
       a = fmaf(Mr[i].z, q.z, a);
       a = fmaf(Mr[i].w, q.w, a);
-      if (!embed_only) xc[i] += a;
+      if (embed_only != 1) xc[i] += a;
     }
     store_tok(xrow + (size_t)l * PF_D, j, xc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_row_attn_combo: block-0 row attention for residue-code inputs (the normal case), from residue-PAIR tables.
+// x0[l] = T[a_l] + T[b_l] takes one of only 22 x 22 = 484 values ("combos") along a pair-row, so everything the
+// row attention needs per token -- LN(x0), k~, q~ -- is a function of the combo and is tabulated once per
+// checkpoint (pf_create, fp64 on the host: Row0Tab).  Per pair-row (one CTA):
+//   1. histogram of the row's combos (integer shared-memory atomics: exact, order-free)
+//   2. sums over the PRESENT combos in ascending combo order: S[h][c] = sum cnt K[h] N[c], sum k~, sum q~
+//   3. row_finalize (as every row kernel): M_row, L / sum q~
+//   4. Y[combo] = x0 + M qhat + bo for the present combos (R0_YCAP at a time), then the row is written by a pure
+//      shared-memory gather + coalesced 16-byte stores: the only per-token work left is the 256-byte write
+// against ~1.1 k instructions per token in k_row_attn<1> (3.1 ms for a write-only 5.1 GB pass at 200 x 1000).
+// Identical sequence pairs give bit-identical rows by construction.
+// ------------------------------------------------------------------------------------------
+#define PF_NCOMBO (PF_NCHAR * PF_NCHAR)
+#define R0_YCAP 128
+#define R0_MAXP 256              // unordered residue pairs: 22 * 23 / 2 = 253 distinct combos at most
+struct Row0Tab {
+  float kq[PF_NCOMBO][8];      // k~[4] | q~[4] = phi(wqk . LN(x0) + bqk)
+  float n[PF_NCOMBO][PF_D];    // LN(x0), no affine
+};
+struct Row0Smem {
+  RowSmem r;                   // tot / ubar / ctx / M / qinv / table; r.red is the 4-way partial buffer of step 2
+  float Y[R0_YCAP][PF_D];
+  float pk[R0_MAXP][8];        // per present combo (list order): cnt k~[4] | cnt q~[4]
+  float qh[R0_MAXP][4];        // per present combo: q~[4] (for Y)
+  int cnt[PF_NCOMBO];
+  short slot_of[PF_NCOMBO];
+  short list[R0_MAXP];
+  int n_present;
+};
+inline size_t row0_smem_bytes(int L) { return sizeof(Row0Smem) + (((size_t)L * 2 + 15) & ~(size_t)15); }
+
+__global__ void __launch_bounds__(256, 3)
+k_row_attn_combo(const PfAttnW* __restrict__ W, const PfHeadW* __restrict__ hw, const Row0Tab* __restrict__ tab,
+                 float* __restrict__ x, const uint8_t* __restrict__ msa, const int* __restrict__ soft_flag, int n, int L,
+                 long long pair_lo, int Pl) {
+  if (soft_flag != nullptr && *soft_flag != 0) return;      // soft (non one-hot) input: k_row_attn<1> does this row
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Row0Smem& sm = *reinterpret_cast<Row0Smem*>(smem_raw);
+  unsigned short* tslot = reinterpret_cast<unsigned short*>(smem_raw + sizeof(Row0Smem));   // [L]: combo, then its slot
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int row = blockIdx.x;
+  const int b = row / Pl, pl = row - b * Pl;
+  float* xrow = x + (size_t)row * L * PF_D;
+  int pi, pj;
+  pair_to_ij(pair_lo + pl, n, &pi, &pj);
+  const uint8_t* si = msa + ((size_t)b * n + pi) * L;
+  const uint8_t* sj = msa + ((size_t)b * n + pj) * L;
+  for (int t = tid; t < PF_NCHAR * PF_D; t += 256) (&sm.r.table[0][0])[t] = (&hw->table[0][0])[t];
+  for (int t = tid; t < PF_NCOMBO; t += 256) sm.cnt[t] = 0;
+  __syncthreads();
+  // ---- 1. histogram; a combo is the UNORDERED residue pair (x0 = T[a] + T[b] is symmetric), so that the pairs
+  //         (i, k) and (k, j) of identical sequences i, j walk the same combos in the same order: bit-identical rows
+  for (int l = tid; l < L; l += 256) {
+    const int u = min((int)si[l], PF_NCHAR - 1), v = min((int)sj[l], PF_NCHAR - 1);
+    const int c = min(u, v) * PF_NCHAR + max(u, v);
+    tslot[l] = (unsigned short)c;
+    atomicAdd(&sm.cnt[c], 1);
+  }
+  __syncthreads();
+  if (tid < 32) {   // present combos, ascending (ballot scan by one warp)
+    int base = 0;
+    for (int c0 = 0; c0 < PF_NCOMBO; c0 += 32) {
+      const int c = c0 + lane;
+      const bool on = c < PF_NCOMBO && sm.cnt[c] > 0;
+      const unsigned bal = __ballot_sync(PF_FULL, on);
+      const int pos = base + __popc(bal & ((1u << lane) - 1u));
+      if (on) { sm.list[pos] = (short)c; sm.slot_of[c] = (short)pos; }
+      base += __popc(bal);
+    }
+    if (lane == 0) sm.n_present = base;
+  }
+  __syncthreads();
+  const int np = sm.n_present;
+  for (int t = tid; t < np * 8; t += 256) {      // the present combos' k~ / q~ (independent loads, one L2 round trip)
+    const int i = t >> 3, v = t & 7, c = sm.list[i];
+    const float kq = __ldg(&tab->kq[c][v]);
+    sm.pk[i][v] = (float)sm.cnt[c] * kq;
+    if (v >= 4) sm.qh[i][v - 4] = kq;
+  }
+  for (int l = tid; l < L; l += 256) tslot[l] = (unsigned short)sm.slot_of[tslot[l]];
+  __syncthreads();
+  // ---- 2. row sums over the present combos: thread (g, c) takes the combos i = g (mod 4) for channel c and all
+  //         four heads; the four partial sums are combined in a fixed order
+  {
+    const int g = tid >> 6, c = tid & 63;
+    float acc[PF_H] = {0.f, 0.f, 0.f, 0.f};
+    int i = g;
+    for (; i + 12 < np; i += 16) {
+      float nv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) nv[u] = __ldg(&tab->n[sm.list[i + 4 * u]][c]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 w = *reinterpret_cast<const float4*>(sm.pk[i + 4 * u]);
+        acc[0] = fmaf(w.x, nv[u], acc[0]); acc[1] = fmaf(w.y, nv[u], acc[1]);
+        acc[2] = fmaf(w.z, nv[u], acc[2]); acc[3] = fmaf(w.w, nv[u], acc[3]);
+      }
+    }
+    for (; i < np; i += 4) {
+      const float nv = __ldg(&tab->n[sm.list[i]][c]);
+      const float4 w = *reinterpret_cast<const float4*>(sm.pk[i]);
+      acc[0] = fmaf(w.x, nv, acc[0]); acc[1] = fmaf(w.y, nv, acc[1]);
+      acc[2] = fmaf(w.z, nv, acc[2]); acc[3] = fmaf(w.w, nv, acc[3]);
+    }
+#pragma unroll
+    for (int h = 0; h < PF_H; ++h) sm.r.red[g][8 + h * PF_D + c] = acc[h];
+    // sum k~ / sum q~: warp v sums value v over the combos (lane-strided, then a fixed xor tree)
+    float sv = 0.f;
+    for (int k = lane; k < np; k += 32) sv += sm.pk[k][warp];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(PF_FULL, sv, o);
+    if (lane == 0) sm.r.tot[warp] = sv;
+  }
+  __syncthreads();
+  {
+    const int e = 8 + tid;      // 256 entries of S
+    sm.r.tot[e] = ((sm.r.red[0][e] + sm.r.red[1][e]) + sm.r.red[2][e]) + sm.r.red[3][e];
+  }
+  __syncthreads();
+  // ---- 3. M_row, L / sum q~ ----
+  row_finalize(W, sm.r, tid, L);
+  // ---- 4. Y for R0_YCAP present combos at a time, then gather + store ----
+  const int part = tid & 15;                       // this thread's 16-byte piece of a token: channels 4 part ..
+  const float4 bo4 = *reinterpret_cast<const float4*>(&W->bo[4 * part]);
+  const float4 M0 = *reinterpret_cast<const float4*>(sm.r.M[4 * part + 0]);
+  const float4 M1 = *reinterpret_cast<const float4*>(sm.r.M[4 * part + 1]);
+  const float4 M2 = *reinterpret_cast<const float4*>(sm.r.M[4 * part + 2]);
+  const float4 M3 = *reinterpret_cast<const float4*>(sm.r.M[4 * part + 3]);
+  const float4 qi = *reinterpret_cast<const float4*>(sm.r.qinv);
+  for (int s0 = 0; s0 < np; s0 += R0_YCAP) {
+    const int ns = min(R0_YCAP, np - s0);
+    for (int idx = tid; idx < ns * 16; idx += 256) {
+      const int sl = idx >> 4, c = sm.list[s0 + sl];
+      const int a = c / PF_NCHAR, bb = c - a * PF_NCHAR;
+      const float4 ta = *reinterpret_cast<const float4*>(&sm.r.table[a][4 * part]);
+      const float4 tb = *reinterpret_cast<const float4*>(&sm.r.table[bb][4 * part]);
+      float4 q = *reinterpret_cast<const float4*>(sm.qh[s0 + sl]);
+      q.x *= qi.x; q.y *= qi.y; q.z *= qi.z; q.w *= qi.w;
+      float4 y;
+      y.x = (ta.x + tb.x) + fmaf(M0.w, q.w, fmaf(M0.z, q.z, fmaf(M0.y, q.y, fmaf(M0.x, q.x, bo4.x))));
+      y.y = (ta.y + tb.y) + fmaf(M1.w, q.w, fmaf(M1.z, q.z, fmaf(M1.y, q.y, fmaf(M1.x, q.x, bo4.y))));
+      y.z = (ta.z + tb.z) + fmaf(M2.w, q.w, fmaf(M2.z, q.z, fmaf(M2.y, q.y, fmaf(M2.x, q.x, bo4.z))));
+      y.w = (ta.w + tb.w) + fmaf(M3.w, q.w, fmaf(M3.z, q.z, fmaf(M3.y, q.y, fmaf(M3.x, q.x, bo4.w))));
+      *reinterpret_cast<float4*>(&sm.Y[sl][4 * part]) = y;
+    }
+    __syncthreads();
+    // 16 threads per token (one 256-byte line per half-warp), four tokens in flight per thread
+    int l = tid >> 4;
+    for (; l + 48 < L; l += 64) {
+      int sl[4];
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) sl[u] = (int)tslot[l + 16 * u] - s0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (sl[u] >= 0 && sl[u] < ns) v[u] = *reinterpret_cast<const float4*>(&sm.Y[sl[u]][4 * part]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (sl[u] >= 0 && sl[u] < ns) *reinterpret_cast<float4*>(xrow + (size_t)(l + 16 * u) * PF_D + 4 * part) = v[u];
+    }
+    for (; l < L; l += 16) {
+      const int sl = (int)tslot[l] - s0;
+      if (sl >= 0 && sl < ns)
+        *reinterpret_cast<float4*>(xrow + (size_t)l * PF_D + 4 * part) = *reinterpret_cast<const float4*>(&sm.Y[sl][4 * part]);
+    }
+    __syncthreads();
   }
 }
 
@@ -566,13 +737,10 @@ k_col_partial(const PfAttnW* __restrict__ W, const float* __restrict__ x, float*
 //   W_v in registers and reuses it for its sites (one 16 KB weight read per CTA instead of per
 //   site; batches of small alignments have tens of thousands of sites).  Summation orders are
 //   fixed and independent of the site's position in the CTA.
-__global__ void __launch_bounds__(256)
-k_col_reduce(const PfAttnW* __restrict__ W, const float* __restrict__ part, int n_chunks, int n_sites, int spc,
-             float* __restrict__ colsum) {
-  __shared__ float tot[PF_FS][PF_PART];
-  __shared__ float ub[PF_FS][PF_H][PF_D];
-  const int t = threadIdx.x, s0 = blockIdx.x * spc;   // spc <= PF_FS sites per CTA
-  const int ns = min(spc, n_sites - s0);
+__device__ __forceinline__ void col_reduce_sites(const PfAttnW* __restrict__ W, const float* __restrict__ part, int n_chunks,
+                                                 int n_sites, int s0, int ns, float* __restrict__ colsum,
+                                                 float (*tot)[PF_PART], float (*ub)[PF_H][PF_D]) {
+  const int t = threadIdx.x;
   for (int i = t; i < ns * PF_PART; i += 256) {
     const int sl = i / PF_PART, e = i - sl * PF_PART;
     float a = 0.f;
@@ -597,6 +765,15 @@ k_col_reduce(const PfAttnW* __restrict__ W, const float* __restrict__ part, int 
     for (int k = 0; k < PF_D; ++k) acc = fmaf(wv[k], ub[sl][h][k], acc);
     colsum[(size_t)(s0 + sl) * PF_COLSUM + 8 + o] = acc;
   }
+}
+
+__global__ void __launch_bounds__(256)
+k_col_reduce(const PfAttnW* __restrict__ W, const float* __restrict__ part, int n_chunks, int n_sites, int spc,
+             float* __restrict__ colsum) {
+  __shared__ float tot[PF_FS][PF_PART];
+  __shared__ float ub[PF_FS][PF_H][PF_D];
+  const int s0 = blockIdx.x * spc;   // spc <= PF_FS sites per CTA
+  col_reduce_sites(W, part, n_chunks, n_sites, s0, min(spc, n_sites - s0), colsum, tot, ub);
 }
 
 // Column attention, step 3 (after the cross-shard sum): ctx = kv / sum k,  M_l = Wo[:,h] ctx_h,
@@ -816,7 +993,7 @@ k_colapply_ffn_fp32(const PfAttnW* __restrict__ Wc, const PfFfnW* __restrict__ W
 // ------------------------------------------------------------------------------------------
 // Pair-sharded column attention over NVLink peer memory (no NCCL on the data path).
 // Every rank owns a symmetric exchange buffer, mapped into all peers:
-//     [ flags: 64 x uint32 ][ slot 0: B*L*72 floats ][ slot 1: B*L*72 floats ]
+//     [ flags: PF_PEER_MAX_WORLD x PF_PEER_MAX_CTAS x uint32 ][ slot 0: B*L*72 floats ][ slot 1: B*L*72 floats ]
 // k_col_reduce writes this rank's 72-float summaries into slot (epoch & 1) of its own buffer;
 // k_peer_sync publishes "epoch reached" into every peer's flag word [rank] (system-scope
 // release after a system fence) and waits until all peers have published the same epoch
@@ -825,16 +1002,19 @@ k_colapply_ffn_fp32(const PfAttnW* __restrict__ Wc, const PfFfnW* __restrict__ W
 // rewritten two exchanges later, and a rank only gets past the next exchange's sync after every
 // peer has finished reading the previous one.
 // ------------------------------------------------------------------------------------------
-#define PF_PEER_FLAG_BYTES 256
+#define PF_PEER_MAX_CTAS 512                               // CTAs of k_col_exchange (one flag word per rank and CTA)
+#define PF_PEER_MAX_WORLD 32
+#define PF_PEER_FLAG_BYTES (PF_PEER_MAX_WORLD * PF_PEER_MAX_CTAS * 4)   // 64 KB
 
 __global__ void k_peer_sync(unsigned char* const* __restrict__ peers, int rank, int world, unsigned epoch,
                             int* __restrict__ err_flag) {
   const int t = threadIdx.x;
   if (t >= world) return;
   __threadfence_system();  // this rank's summaries (written by the previous kernel) before the flag
-  volatile unsigned* remote = reinterpret_cast<volatile unsigned*>(peers[t]) + rank;
+  // three-launch form (PF_EXCH_IMPL=split): one flag per rank, kept in the last CTA column of the flag table
+  volatile unsigned* remote = reinterpret_cast<volatile unsigned*>(peers[t]) + (size_t)rank * PF_PEER_MAX_CTAS + (PF_PEER_MAX_CTAS - 1);
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
-  const unsigned* mine = reinterpret_cast<const unsigned*>(peers[rank]) + t;
+  const unsigned* mine = reinterpret_cast<const unsigned*>(peers[rank]) + (size_t)t * PF_PEER_MAX_CTAS + (PF_PEER_MAX_CTAS - 1);
   unsigned v = 0;
   for (unsigned spin = 0; spin < (1u << 26); ++spin) {   // bounded (~seconds): never hang the GPU
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
@@ -861,6 +1041,80 @@ k_col_finalize_peer(const PfAttnW* __restrict__ W, unsigned char* const* __restr
   }
   __syncthreads();
   col_finalize_sites(W, tot, ns, s0, p_total, colM, ctx);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_col_exchange: chunk reduce + cross-rank exchange + finalize of the column summaries in ONE launch per block
+// (replaces k_col_reduce -> k_peer_sync -> k_col_finalize_peer, and k_col_reduce -> k_col_finalize on one GPU).
+// The exchange is site-chunked: CTA c owns the site groups c, c + grid, ... (spc sites each; the same grid on every
+// rank), and the flag that guards a peer's data is per (rank, CTA), not per rank:
+//   phase 1  reduce the pair-chunk partials of my site groups into the 72-float exchange form, in my own slot of
+//            the symmetric buffer (plain stores to local HBM)
+//   publish  CTA barrier, system fence, st.release.sys of the epoch into flag [rank][c] of every peer
+//   phase 2  ld.acquire.sys until flag [r][c] of every rank r shows the epoch, then read the same site groups out of
+//            every rank's slot over NVLink (L1-bypassing loads), sum in rank order (bit-identical on all ranks),
+//            finalize M_l / qinv
+// No CTA waits before it has published everything it owns, so the kernel cannot deadlock whatever order the CTAs
+// are scheduled in, and the NVLink latency of the first groups' flags and data hides behind the reduction of the
+// other groups and CTAs instead of behind a device-wide kernel boundary (the three-launch form's two boundaries
+// and its single-warp sync kernel were 5 % of a step at 8 ranks).  Slot reuse: as above, two slots.
+// ------------------------------------------------------------------------------------------
+struct ColExSmem {
+  union {
+    struct { float tot[PF_FS][PF_PART]; float ub[PF_FS][PF_H][PF_D]; } a;      // phase 1
+    struct { float tot[PF_FS][PF_COLSUM]; float ctx[PF_FS][PF_D]; } b;         // phase 2
+  };
+};
+
+__global__ void __launch_bounds__(256)
+k_col_exchange(const PfAttnW* __restrict__ W, const float* __restrict__ part, int n_chunks, int n_sites, int spc,
+               float* __restrict__ my_slot, unsigned char* const* __restrict__ peers, int rank, int world, int slot,
+               size_t slot_floats, unsigned epoch, float p_total, float* __restrict__ colM, int* __restrict__ err_flag) {
+  __shared__ ColExSmem sm;
+  const int t = threadIdx.x;
+  const int n_groups = (n_sites + spc - 1) / spc;
+  for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+    const int s0 = g * spc;
+    col_reduce_sites(W, part, n_chunks, n_sites, s0, min(spc, n_sites - s0), my_slot, sm.a.tot, sm.a.ub);
+    __syncthreads();
+  }
+  if (world > 1) {
+    __syncthreads();
+    if (t < world) {
+      __threadfence_system();   // the CTA's summaries (ordered before this thread by the barrier) before the flag
+      unsigned* remote = reinterpret_cast<unsigned*>(peers[t]) + (size_t)rank * PF_PEER_MAX_CTAS + blockIdx.x;
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+      const unsigned* mine = reinterpret_cast<const unsigned*>(peers[rank]) + (size_t)t * PF_PEER_MAX_CTAS + blockIdx.x;
+      unsigned v = 0;
+      bool ok = false;
+      for (unsigned spin = 0; spin < (1u << 26); ++spin) {   // bounded (~seconds): never hang the GPU
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+        if ((int)(v - epoch) >= 0) { ok = true; break; }
+        __nanosleep(32);
+      }
+      if (!ok && err_flag != nullptr) *err_flag = 3;
+    }
+    __syncthreads();
+  }
+  for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+    const int s0 = g * spc, ns = min(spc, n_sites - s0);
+    for (int i = t; i < ns * PF_COLSUM; i += 256) {
+      float a;
+      if (world > 1) {
+        a = 0.f;
+        for (int r = 0; r < world; ++r) {  // fixed rank order
+          const float* src = reinterpret_cast<const float*>(peers[r] + PF_PEER_FLAG_BYTES) + (size_t)slot * slot_floats;
+          a += __ldcg(src + (size_t)s0 * PF_COLSUM + i);
+        }
+      } else {
+        a = my_slot[(size_t)s0 * PF_COLSUM + i];
+      }
+      (&sm.b.tot[0][0])[i] = a;
+    }
+    __syncthreads();
+    col_finalize_sites(W, sm.b.tot, ns, s0, p_total, colM, sm.b.ctx);
+    __syncthreads();
+  }
 }
 
 __global__ void __launch_bounds__(256)

@@ -196,6 +196,11 @@ class Phyloformer(nn.Module):
         if self._peer is not None and self._peer[2] >= need_floats:
             if self._peer[3] != self._handle_gen:   # the handle was re-created (weights changed): bind the same buffers again
                 buf, hdl, slot, _ = self._peer
+                torch.cuda.synchronize(device)
+                dist.barrier(group)       # nobody still reads the old epochs' flags or slots
+                buf.zero_()               # the new handle counts its exchange epochs from zero again
+                torch.cuda.synchronize(device)
+                dist.barrier(group)
                 ptrs = (ctypes.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
                 _cabi.check(lib.pf_set_peer_exchange(self._handle, rank, world, ptrs, slot), "pf_set_peer_exchange")
                 self._peer = (buf, hdl, slot, self._handle_gen)

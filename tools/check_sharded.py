@@ -45,8 +45,18 @@ def main():
         ref = [torch.empty_like(a) for _ in range(world)]
         dist.all_gather(ref, a)
         assert all(torch.equal(r, a) for r in ref), "ranks disagree"
+    # a weight update re-creates the native handle: the peer buffers are re-bound (flags zeroed, epochs restart)
+    m.shard_pairs(exchange="p2p")
+    before = m.forward_idx(idx, squeeze=False)
+    with torch.no_grad():
+        m.pwFNN[0].bias.add_(0.0)
+    after = m.forward_idx(idx, squeeze=False)
+    after2 = m.forward_idx(idx, squeeze=False)
+    m.check_device_error()
+    assert torch.equal(before, after) and torch.equal(after, after2), "re-bound peer exchange differs"
     if rank == 0:
-        print(f"sharded == unsharded on {world} ranks (p2p and nccl), worst max-rel {worst:.2e}")
+        print(f"sharded == unsharded on {world} ranks (p2p and nccl), worst max-rel {worst:.2e}; exchange impl "
+              f"{os.environ.get('PF_EXCH_IMPL', 'fused')}")
     dist.destroy_process_group()
 
 

@@ -26,7 +26,10 @@ for step in "$@"; do
     head)    timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "fused_head or stage_taps or synthetic_shapes or tcgen05_ffn or forward_idx_equals" -s > $out/pytest_head.txt 2>&1; echo "rc=$?" >> $out/pytest_head.txt ;;
     lean)    PF_LIB=build/libpf_lean.so timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "fused_head or stage_taps or synthetic_shapes or forward_idx_equals" -s > $out/pytest_lean.txt 2>&1; echo "rc=$?" >> $out/pytest_lean.txt ;;
     ab)      tools/ab_bench.sh ${AB_REPS:-2} phyloformer_b200/libpf_sm100.so $AB_LIBS > $out/ab.txt 2>&1 ;;
-    quick)   timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "tensor_core_attention or fused_head or stage_taps or cuda_graph or cli_end or reference_cases" -s > $out/pytest_quick.txt 2>&1; echo "rc=$?" >> $out/pytest_quick.txt ;;
+    sharded) timeout 900 python -m pytest tests/test_gpu_sharded.py -x -q -m gpu -s > $out/pytest_sharded.txt 2>&1; echo "rc=$?" >> $out/pytest_sharded.txt ;;
+    ab_exch) ( tools/ab_bench.sh 2 phyloformer_b200/libpf_sm100.so; echo split; PF_EXCH_IMPL=split tools/ab_bench.sh 2 phyloformer_b200/libpf_sm100.so; echo 256x20x200; WORKLOAD=256x20x200 tools/ab_bench.sh 2 phyloformer_b200/libpf_sm100.so; echo split; WORKLOAD=256x20x200 PF_EXCH_IMPL=split tools/ab_bench.sh 2 phyloformer_b200/libpf_sm100.so ) > $out/ab_exch.txt 2>&1 ;;
+    ab_env)  ( for i in 1 2; do tools/ab_bench.sh 1 phyloformer_b200/libpf_sm100.so; echo "$AB_ENV"; env $AB_ENV tools/ab_bench.sh 1 phyloformer_b200/libpf_sm100.so; done; if [ -n "$AB_WORKLOAD2" ]; then echo $AB_WORKLOAD2; WORKLOAD=$AB_WORKLOAD2 tools/ab_bench.sh 1 phyloformer_b200/libpf_sm100.so; echo "$AB_ENV"; WORKLOAD=$AB_WORKLOAD2 env $AB_ENV tools/ab_bench.sh 1 phyloformer_b200/libpf_sm100.so; fi ) > $out/ab_env.txt 2>&1 ;;
+    quick)   timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "tensor_core_attention or fused_head or stage_taps or cuda_graph or cli_end or reference_cases or block0_combo or duplicate or native_library" -s > $out/pytest_quick.txt 2>&1; echo "rc=$?" >> $out/pytest_quick.txt ;;
     smoke)   timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke.txt 2>&1; echo "rc=$?" >> $out/smoke.txt ;;
     *) echo "unknown step $step" ;;
   esac
