@@ -739,6 +739,10 @@ k_col_partial_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnTcW* __re
 // The item stream of the loader and the P1 warps interleaves the next row's pass A with this row's pass
 // B (lag RW_LAG tiles), so the tensor pipe, the finalize and the apply overlap; D_S, M_row and the q~ cache
 // are double buffered by row parity.
+// Measured and removed (round 2): the apply items on the 8 TMEM-reader warps instead of the P1 warps (which are busy
+// 74 % of the kernel with both passes; the readers 19 %): parity green once both groups observe and release every
+// ring stage, but no faster (15.9 vs 16.0 ms of row time per forward) -- the kernel moves 12.2 GB per launch at 4.5
+// TB/s and is bound by that traffic (2.1 GB of it pass-B re-reads that miss L2), not by any warp role.
 // ------------------------------------------------------------------------------------------
 #define RW_THREADS C2_THREADS
 #define RW_NS 3                                   // staging ring
@@ -1088,8 +1092,15 @@ k_row_attn_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnW* __restric
         for (int e = 0; e < 2; ++e) {
           const int idx = ptid + 128 * e, c = idx >> 2, h = idx & 3;
           float acc = 0.f;
+          const float4* wrow = reinterpret_cast<const float4*>(&W->wo[c][h * PF_DH]);   // 4 x LDG.128 instead of 16 strided LDG.32
 #pragma unroll
-          for (int ee = 0; ee < PF_DH; ++ee) acc = fmaf(W->wo[c][h * PF_DH + ee], ctx[h * PF_DH + ee], acc);
+          for (int e4 = 0; e4 < PF_DH / 4; ++e4) {
+            const float4 w = wrow[e4];
+            acc = fmaf(w.x, ctx[h * PF_DH + 4 * e4 + 0], acc);
+            acc = fmaf(w.y, ctx[h * PF_DH + 4 * e4 + 1], acc);
+            acc = fmaf(w.z, ctx[h * PF_DH + 4 * e4 + 2], acc);
+            acc = fmaf(w.w, ctx[h * PF_DH + 4 * e4 + 3], acc);
+          }
           fin[(c + (c >> 2)) * 4 + h] = acc;
         }
         mbar_arrive(BAR(RW_B_FINDONE + par));

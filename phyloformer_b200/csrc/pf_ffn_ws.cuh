@@ -35,6 +35,11 @@
 // Variants that were built, measured and removed again (DESIGN.md section 3.1 has the numbers):
 // final-row stores by the MMA warpgroup's idle warps, two producer threads per token row
 // (8 producer warps), epilogue warps above the producer in warp-id order.
+// 12 epilogue warps inside the 16-warp CTA (round 2: the MMA warpgroup's issuer and its three idle warps join the
+// epilogue as a third column group, chunks split 3 / 3 / 2, the issuer issuing each GEMM as soon as its inputs are
+// there and never blocking on the producer; no spills): parity green, 36.6 vs 32.5 ms -- the time per 16-column chunk
+// rises by the same 50 % as the number of epilogue warps per scheduler, i.e. a scheduler's two epilogue warps already
+// take everything it can issue for this instruction mix (packed FFMA2 / half-rate ALU / MUFU); more warps cannot help.
 // 16 epilogue warps at <= 80 registers with a row-chunked producer (x2 staged through TMEM, 12 extra TMEM
 // instructions per row): built and measured in round 2, 34.7 vs 32.5 ms of FFN time per forward -> removed.
 #define WS_NCG (WS_EW / 4)            // epilogue column groups per TMEM lane quadrant

@@ -95,8 +95,15 @@ __device__ __forceinline__ void row_finalize(const PfAttnW* __restrict__ W, RowS
   {
     const int c = tid >> 2, h = tid & 3;
     float acc = 0.f;
+    const float4* wrow = reinterpret_cast<const float4*>(&W->wo[c][h * PF_DH]);   // 4 x LDG.128 (a thread's 16 weights are 64 contiguous bytes)
 #pragma unroll
-    for (int e = 0; e < PF_DH; ++e) acc = fmaf(W->wo[c][h * PF_DH + e], sm.ctx[h * PF_DH + e], acc);
+    for (int e4 = 0; e4 < PF_DH / 4; ++e4) {
+      const float4 w = wrow[e4];
+      acc = fmaf(w.x, sm.ctx[h * PF_DH + 4 * e4 + 0], acc);
+      acc = fmaf(w.y, sm.ctx[h * PF_DH + 4 * e4 + 1], acc);
+      acc = fmaf(w.z, sm.ctx[h * PF_DH + 4 * e4 + 2], acc);
+      acc = fmaf(w.w, sm.ctx[h * PF_DH + 4 * e4 + 3], acc);
+    }
     sm.M[c][h] = acc;
   }
   __syncthreads();
@@ -330,7 +337,12 @@ k_row_attn_combo(const PfAttnW* __restrict__ W, const PfHeadW* __restrict__ hw, 
   pair_to_ij(pair_lo + pl, n, &pi, &pj);
   const uint8_t* si = msa + ((size_t)b * n + pi) * L;
   const uint8_t* sj = msa + ((size_t)b * n + pj) * L;
-  for (int t = tid; t < PF_NCHAR * PF_D; t += 256) (&sm.r.table[0][0])[t] = (&hw->table[0][0])[t];
+  float treg[(PF_NCHAR * PF_D + 255) / 256];      // the embedding table travels through registers: its load latency
+#pragma unroll                                    // hides behind the histogram instead of sitting in front of it
+  for (int k = 0; k < (PF_NCHAR * PF_D + 255) / 256; ++k) {
+    const int t = tid + 256 * k;
+    treg[k] = t < PF_NCHAR * PF_D ? __ldg(&hw->table[0][0] + t) : 0.f;
+  }
   for (int t = tid; t < PF_NCOMBO; t += 256) sm.cnt[t] = 0;
   __syncthreads();
   // ---- 1. histogram; a combo is the UNORDERED residue pair (x0 = T[a] + T[b] is symmetric), so that the pairs
@@ -340,6 +352,11 @@ k_row_attn_combo(const PfAttnW* __restrict__ W, const PfHeadW* __restrict__ hw, 
     const int c = min(u, v) * PF_NCHAR + max(u, v);
     tslot[l] = (unsigned short)c;
     atomicAdd(&sm.cnt[c], 1);
+  }
+#pragma unroll
+  for (int k = 0; k < (PF_NCHAR * PF_D + 255) / 256; ++k) {
+    const int t = tid + 256 * k;
+    if (t < PF_NCHAR * PF_D) (&sm.r.table[0][0])[t] = treg[k];
   }
   __syncthreads();
   if (tid < 32) {   // present combos, ascending (ballot scan by one warp)
@@ -743,9 +760,20 @@ __device__ __forceinline__ void col_reduce_sites(const PfAttnW* __restrict__ W, 
   const int t = threadIdx.x;
   for (int i = t; i < ns * PF_PART; i += 256) {
     const int sl = i / PF_PART, e = i - sl * PF_PART;
-    float a = 0.f;
-    for (int ch = 0; ch < n_chunks; ++ch) a += part[((size_t)ch * n_sites + s0 + sl) * PF_PART + e];
-    tot[sl][e] = a;
+    // four interleaved chains (chunks ch = k mod 4), combined in a fixed order: the loads of a chain of n_chunks
+    // dependent adds were the latency of this kernel
+    const float* src = part + ((size_t)s0 + sl) * PF_PART + e;
+    const size_t cs = (size_t)n_sites * PF_PART;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int ch = 0;
+    for (; ch + 3 < n_chunks; ch += 4) {
+      const float v0 = src[(size_t)ch * cs], v1 = src[(size_t)(ch + 1) * cs], v2 = src[(size_t)(ch + 2) * cs], v3 = src[(size_t)(ch + 3) * cs];
+      a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+    }
+    if (ch < n_chunks) a0 += src[(size_t)ch * cs];
+    if (ch + 1 < n_chunks) a1 += src[(size_t)(ch + 1) * cs];
+    if (ch + 2 < n_chunks) a2 += src[(size_t)(ch + 2) * cs];
+    tot[sl][e] = (a0 + a1) + (a2 + a3);
   }
   __syncthreads();
   for (int i = t; i < ns * PF_H * PF_D; i += 256) {

@@ -24,7 +24,7 @@ m.forward_idx(idx)
 torch.cuda.synchronize()
 t = dump[128 * 320:].view(148, 3, 8).cpu()
 P = n * (n - 1) // 2
-tiles = ((L + 15) // 16) * ((P + 7) // 8) / 148.0
+tiles = ((L + 3) // 4) * ((P + 31) // 32) / 148.0      # 32 pairs x 4 sites per tile (WS_G x WS_S)
 names = {0: ("producer", ["a1_free", "d2_free", "load+LN1", "wait_st", "-", "-", "-"]),
          1: ("mma", ["a1_full", "h_full[a]", "h_full[b]", "issue_g1", "issue_g2", "-", "-"]),
          2: ("epilogue", ["g1_done[a]", "g1_done[b]", "g2_done", "wait_ld", "wait_st", "e2", "-"])}
