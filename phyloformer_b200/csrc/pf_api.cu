@@ -333,6 +333,7 @@ int pf_create(pf_handle* out, const pf_cfg* cfg, const float* const* weights_dev
       kc.whead[c] = head[0].whead[c];
     }
     kc.bhead = head[0].bhead;
+    for (int jj = 0; jj < PF_HID; ++jj) kc.b1[jj] = blk[b].ffn.b1[jj];
     kc.pad[0] = kc.pad[1] = kc.pad[2] = 0.f;
     for (int hh = 0; hh < PF_H; ++hh) kc.bq[hh] = blk[b].col.bqk[4 + hh];
     h->ffn_const.push_back(kc);

@@ -42,6 +42,14 @@
 // take everything it can issue for this instruction mix (packed FFMA2 / half-rate ALU / MUFU); more warps cannot help.
 // 16 epilogue warps at <= 80 registers with a row-chunked producer (x2 staged through TMEM, 12 extra TMEM
 // instructions per row): built and measured in round 2, 34.7 vs 32.5 ms of FFN time per forward -> removed.
+// WS_B1_CONST = 1: the epilogue reads b1 through the constant bank (LDC) instead of shared memory, whose loads queue
+// behind the previous chunk's tcgen05.st in the MIO queue
+#ifndef WS_ST16
+#define WS_ST16 1   // one tcgen05.st.x16 per chunk (hi | lo words are adjacent columns) instead of two .x8
+#endif
+#ifndef WS_B1_CONST
+#define WS_B1_CONST 1
+#endif
 #define WS_NCG (WS_EW / 4)            // epilogue column groups per TMEM lane quadrant
 #define WS_NPW 4                      // producer warps
 #define WS_PW0 WS_EW                  // first producer warp
@@ -78,6 +86,7 @@ struct PfFfnConst {
   float whead[PF_D];     // pwFNN.0.weight (HEAD instantiation: the last block's launch emits distances)
   float bhead;
   float pad[3];
+  float b1[PF_HID];      // folded ffn.0 bias: read by the epilogue through the constant bank (WS_B1_CONST)
 };
 
 typedef pf_u64 u64;  // packed fp32 pair helpers (pk2, up2, fma2, mul2, add2) live in pf_common.cuh
@@ -505,12 +514,24 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float h0, h1;   // one packed add for the pair's bias
+#if WS_B1_CONST
+          up2(add2(pk2(__uint_as_float(vc[2 * i]), __uint_as_float(vc[2 * i + 1])),
+                   pk2(kc.b1[cc + 2 * i], kc.b1[cc + 2 * i + 1])), h0, h1);
+#else
           up2(add2(pk2(__uint_as_float(vc[2 * i]), __uint_as_float(vc[2 * i + 1])),
                    *reinterpret_cast<const u64*>(sb1 + cc + 2 * i)), h0, h1);
+#endif
           cvt2<FMT>(gelu_fast2(h0, h1), hi[i], lo[i]);
         }
-        tmem_st8(tmem + lane_base + cc, hi);
-        if (FMT == WS_FMT_BF16X3) tmem_st8(tmem + lane_base + cc + 8, lo);
+        if (WS_ST16 && FMT == WS_FMT_BF16X3) {   // hi words in columns cc..cc+7, lo words in cc+8..cc+15: one 16-column store
+          uint32_t hl[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { hl[i] = hi[i]; hl[8 + i] = lo[i]; }
+          tmem_st16(tmem + lane_base + cc, hl);
+        } else {
+          tmem_st8(tmem + lane_base + cc, hi);
+          if (FMT == WS_FMT_BF16X3) tmem_st8(tmem + lane_base + cc + 8, lo);
+        }
       };
       const int n_mine = (8 - chf + WS_NCG - 1) / WS_NCG;   // chunks of this warp in a half
       tmem_ld16(tmem + lane_base + col_of(0), v[0]);

@@ -29,6 +29,7 @@ for step in "$@"; do
     sharded) timeout 900 python -m pytest tests/test_gpu_sharded.py -x -q -m gpu -s > $out/pytest_sharded.txt 2>&1; echo "rc=$?" >> $out/pytest_sharded.txt ;;
     ab_exch) ( tools/ab_bench.sh 2 phyloformer_b200/libpf_sm100.so; echo split; PF_EXCH_IMPL=split tools/ab_bench.sh 2 phyloformer_b200/libpf_sm100.so; echo 256x20x200; WORKLOAD=256x20x200 tools/ab_bench.sh 2 phyloformer_b200/libpf_sm100.so; echo split; WORKLOAD=256x20x200 PF_EXCH_IMPL=split tools/ab_bench.sh 2 phyloformer_b200/libpf_sm100.so ) > $out/ab_exch.txt 2>&1 ;;
     ab_env)  ( for i in 1 2; do tools/ab_bench.sh 1 phyloformer_b200/libpf_sm100.so; echo "$AB_ENV"; env $AB_ENV tools/ab_bench.sh 1 phyloformer_b200/libpf_sm100.so; done; if [ -n "$AB_WORKLOAD2" ]; then echo $AB_WORKLOAD2; WORKLOAD=$AB_WORKLOAD2 tools/ab_bench.sh 1 phyloformer_b200/libpf_sm100.so; echo "$AB_ENV"; WORKLOAD=$AB_WORKLOAD2 env $AB_ENV tools/ab_bench.sh 1 phyloformer_b200/libpf_sm100.so; fi ) > $out/ab_env.txt 2>&1 ;;
+    sanit)   timeout 1500 compute-sanitizer --tool memcheck --print-limit 5 python tools/sanitize_smoke.py > $out/sanitizer.txt 2>&1; echo "rc=$?" >> $out/sanitizer.txt ;;
     quick)   timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "tensor_core_attention or fused_head or stage_taps or cuda_graph or cli_end or reference_cases or block0_combo or duplicate or native_library" -s > $out/pytest_quick.txt 2>&1; echo "rc=$?" >> $out/pytest_quick.txt ;;
     smoke)   timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke.txt 2>&1; echo "rc=$?" >> $out/smoke.txt ;;
     *) echo "unknown step $step" ;;
