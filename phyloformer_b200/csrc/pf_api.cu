@@ -390,6 +390,20 @@ int pf_create(pf_handle* out, const pf_cfg* cfg, const float* const* weights_dev
   if (const char* e_ex = getenv("PF_EXCH_IMPL")) h->exch_impl = (strcmp(e_ex, "split") == 0) ? 0 : 1;
   if (const char* e_hd = getenv("PF_HEAD_IMPL")) h->head_impl = (strcmp(e_hd, "sep") == 0) ? 0 : 1;
   if (const char* e_col = getenv("PF_COL_IMPL")) h->col_impl = (strcmp(e_col, "cc") == 0) ? 0 : (strcmp(e_col, "tc1") == 0) ? 1 : 2;
+  // Load every kernel that spins on (or is waited for by) a peer NOW: with CUDA's lazy module loading a first launch can
+  // block the host until the device is idle, i.e. until a peer-wait kernel already running on it has timed out
+  // (seen with two ranks driven from one process: tests/test_gpu_peer_emulated.py).
+  {
+    cudaFuncAttributes fa;
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_col_exchange));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_col_reduce));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_peer_sync));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_col_finalize_peer));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_col_finalize));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_head_reduce));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_head));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_col_partial));
+  }
   int rc = pf_ffn_tc_init();
   if (rc == 0) rc = pf_ffn_ws_init();
   if (rc == 0) rc = pf_attn_tc_init();
