@@ -747,7 +747,11 @@ k_col_partial_ws(const __grid_constant__ CUtensorMap tmap, const PfAttnTcW* __re
 #define RW_THREADS C2_THREADS
 #define RW_NS 3                                   // staging ring
 #define RW_NA 2                                   // operand image / k~ operand / D_qk ring
-#define RW_LAG 3
+#ifndef RW_LAG
+#define RW_LAG 1                                  // pass B of row i-1 starts this many tiles into row i.  Measured row time per
+#endif                                            // forward at lag 5 / 3 / 2 / 1 / 0: 17.1 / 16.4 / 15.9 / 15.3 / 15.5 ms: every tile
+                                                  // between a tile's first read and its re-read costs L2 hits (0 exposes the finalize).
+                                                  // Two pass-B items per pass-A item (re-read over after half a row): 17.3 ms.
 // Order in which pass B walks the tiles of a row.  Reverse (last tile first): the tiles pass A staged last are
 // the ones most likely to be L2 hits when the re-read starts, so the part of the row that does fall out of L2 is
 // re-fetched once instead of pushing the still-unread part out ahead of the read pointer.

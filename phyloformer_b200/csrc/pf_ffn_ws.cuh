@@ -40,6 +40,8 @@
 // there and never blocking on the producer; no spills): parity green, 36.6 vs 32.5 ms -- the time per 16-column chunk
 // rises by the same 50 % as the number of epilogue warps per scheduler, i.e. a scheduler's two epilogue warps already
 // take everything it can issue for this instruction mix (packed FFMA2 / half-rate ALU / MUFU); more warps cannot help.
+// (Re-measured after b1 moved to the constant bank: 36.4 vs 29.8 ms.  The issuer now also loses time whenever the
+// producer is the late party: a dedicated MMA warp blocks on a1_full and issues at once, a working one finds out late.)
 // 16 epilogue warps at <= 80 registers with a row-chunked producer (x2 staged through TMEM, 12 extra TMEM
 // instructions per row): built and measured in round 2, 34.7 vs 32.5 ms of FFN time per forward -> removed.
 // WS_B1_CONST = 1: the epilogue reads b1 through the constant bank (LDC) instead of shared memory, whose loads queue
