@@ -42,6 +42,9 @@
 // take everything it can issue for this instruction mix (packed FFMA2 / half-rate ALU / MUFU); more warps cannot help.
 // (Re-measured after b1 moved to the constant bank: 36.4 vs 29.8 ms.  The issuer now also loses time whenever the
 // producer is the late party: a dedicated MMA warp blocks on a1_full and issues at once, a working one finds out late.)
+// Final rows (E2) on the MMA warpgroup instead of the epilogue warps (warps 13..15 for TMEM lane quadrants 1..3, the
+// issuer for quadrant 0 right after a tile's last issue): parity green, 31.2 vs 30.1 ms -- E1 slows down by what E2
+// took: the work per SM is conserved whichever warps do it (TMEM / MIO path, not warp latency).
 // 16 epilogue warps at <= 80 registers with a row-chunked producer (x2 staged through TMEM, 12 extra TMEM
 // instructions per row): built and measured in round 2, 34.7 vs 32.5 ms of FFN time per forward -> removed.
 // WS_B1_CONST = 1: the epilogue reads b1 through the constant bank (LDC) instead of shared memory, whose loads queue
