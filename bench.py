@@ -16,9 +16,13 @@ scaling.  Prints ONE JSON line (rank 0).
   e2e        the same metric through the reference-facing call: host (pinned) fp32 one-hot
              (B,22,L,n) -> .cuda() -> model(x) -> .cpu(), copies inside the timed region
   roofline   the dominant kernel (column-apply + LN + FFN + residual), timed live with CUDA
-             events around each launch (pf_profile_*), against MEASURED_PEAKS.json
-  cpu_baseline  the CPU oracle (a torch-CPU restatement of the reference graph: "port") on a
-             bounded sample of the same workload, on this box's host cores
+             events around each launch (pf_profile_*), against MEASURED_PEAKS.json; roofline.kernels
+             holds the same for the row / column-summary kernels against the HBM peak
+  cpu_baseline  the unmodified reference module (baseline/_ref, staged by tools/stage_ref.sh; the CPU
+             oracle port when it is absent) on a bounded sample of the same workload, on this box's
+             host cores
+  checks     parity of what was just timed: against the full-size fp64 oracle fixture, and at N > 1
+             against the unsharded forward and across ranks (bit equality)
 """
 import argparse
 import json
@@ -441,6 +445,10 @@ def run_native(args):
         if tr["workload"] == args.workload and world == tr["n_gpus"] and args.precision != "fp32":
             roofline["traffic"] = tr["dram_bytes_per_launch"]["k_colapply_ffn_ws"]
             roofline["traffic_algorithmic"] = tr["algorithmic_bytes_per_launch"]["k_colapply_ffn_ws"]
+            for cls, kname in (("row", "k_row_attn_ws"), ("colsum", "k_col_partial_ws"), ("ffn", "k_colapply_ffn_ws")):
+                if cls in kernels:      # ncu --set full capture of one launch of the class's kernel (profiles/r02_ncu_summary.txt)
+                    kernels[cls]["traffic"] = tr["dram_bytes_per_launch"][kname]
+                    kernels[cls]["ncu_kernel"] = kname
     except Exception:  # noqa: BLE001
         pass
     roofline.update({"peak_source": peaks["source"] + " (sustained)" if roofline["bound"] == "tensor" else peaks["source"],
