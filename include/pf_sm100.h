@@ -151,7 +151,12 @@ int pf_last_launch_count(pf_handle h);
  * forward.  After this call pf_forward ignores `reduce` for partial pair ranges: the library's
  * own kernels publish, synchronise (system-scope flags) and read the (B,L,72) summaries with
  * plain P2P loads, summing in rank order.  world <= 1 or NULL disables it again.
- * Every rank must issue the same sequence of forwards. */
+ * Every rank must issue the same sequence of forwards (the exchange epochs are counted per
+ * handle from this call on: re-zero the buffers, with a barrier on either side, before binding
+ * them to a new handle).  Buffer layout: 64 KB of flags, one 32-bit word per (rank, exchange CTA)
+ * -- the exchange is site-chunked: a CTA that has reduced its site groups publishes its own flag
+ * and waits only for the same CTA of every peer -- followed by two slots of slot_floats floats.
+ * world <= 32. */
 int pf_set_peer_exchange(pf_handle h, int rank, int world, void* const* peer_bufs_host, size_t slot_floats);
 size_t pf_peer_exchange_bytes(size_t slot_floats);
 
