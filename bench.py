@@ -263,6 +263,7 @@ def run_native(args):
     batch_sharded = world > 1 and B >= world
     if world > 1 and not batch_sharded:
         model.shard_pairs(exchange=args.exchange)
+        model.check_peer_errors = False      # keep the timed forwards asynchronous; the flag is read after the timed regions
     idx_host = pf_oracle.synth_msa(n, L, seed=1337 + n, kind="tree", B=B)
     if batch_sharded:  # independent MSAs: replicas, no collective
         from phyloformer_b200 import sharding
@@ -319,6 +320,7 @@ def run_native(args):
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
         # ---- correctness of what was just timed (outside the timed regions) --------------------
         checks = {}
+        model.check_device_error()      # a bounded device-side wait that timed out invalidates the run: fail loudly
         fx = os.path.join(ROOT, "tests", "golden", f"oracle_fullsize_{n}x{L}.npz")
         if B == 1 and os.path.exists(fx):     # every distance against the pair-chunked fp64 oracle (tests/golden/make_fullsize.py)
             import numpy as np

@@ -107,6 +107,10 @@ class Phyloformer(nn.Module):
         self._peer_failed = False
         self._reduce_cb = None
         self.last_launches = 0
+        # Pair-sharded forwards over the peer-memory exchange end with a (synchronising) read of the device error flag: a
+        # peer that never publishes makes the bounded wait time out, and the result of that call is then invalid.  Set
+        # to False to keep the forward asynchronous and call check_device_error() yourself (bench.py does).
+        self.check_peer_errors = True
 
     # ------------------------------------------------------------------ native handle
     def _weights_key(self):
@@ -297,6 +301,8 @@ class Phyloformer(nn.Module):
             return act
         if self._shard is not None:
             dist_out = self._gather(dist_out, n)
+            if self.check_peer_errors and self._peer is not None:
+                self.check_device_error()
         return dist_out
 
     def _gather(self, local, n):
