@@ -49,6 +49,11 @@
 // instructions per row): built and measured in round 2, 34.7 vs 32.5 ms of FFN time per forward -> removed.
 // WS_B1_CONST = 1: the epilogue reads b1 through the constant bank (LDC) instead of shared memory, whose loads queue
 // behind the previous chunk's tcgen05.st in the MIO queue
+#ifdef WS_DIAG_NO_LDTM   // timing diagnostic only (wrong results): no TMEM reads in E1
+#define E1_LD(addr, arr) do { for (int k_ = 0; k_ < 16; ++k_) (arr)[k_] = (uint32_t)(addr) + k_; } while (0)
+#else
+#define E1_LD(addr, arr) tmem_ld16(addr, arr)
+#endif
 #ifndef WS_ST16
 #define WS_ST16 1   // one tcgen05.st.x16 per chunk (hi | lo words are adjacent columns) instead of two .x8
 #endif
@@ -519,7 +524,9 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float h0, h1;   // one packed add for the pair's bias
-#if WS_B1_CONST
+#if defined(WS_DIAG_NO_B1)
+          up2(pk2(__uint_as_float(vc[2 * i]), __uint_as_float(vc[2 * i + 1])), h0, h1);
+#elif WS_B1_CONST
           up2(add2(pk2(__uint_as_float(vc[2 * i]), __uint_as_float(vc[2 * i + 1])),
                    pk2(kc.b1[cc + 2 * i], kc.b1[cc + 2 * i + 1])), h0, h1);
 #else
@@ -528,6 +535,9 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
 #endif
           cvt2<FMT>(gelu_fast2(h0, h1), hi[i], lo[i]);
         }
+#ifdef WS_DIAG_NO_STTM
+        if (hi[0] == 0x12345678u && lo[3] == 0x9abcdef0u)   // timing diagnostic only: (practically) never stores
+#endif
         if (WS_ST16 && FMT == WS_FMT_BF16X3) {   // hi words in columns cc..cc+7, lo words in cc+8..cc+15: one 16-column store
           uint32_t hl[16];
 #pragma unroll
@@ -539,21 +549,21 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
         }
       };
       const int n_mine = (8 - chf + WS_NCG - 1) / WS_NCG;   // chunks of this warp in a half
-      tmem_ld16(tmem + lane_base + col_of(0), v[0]);
+      E1_LD(tmem + lane_base + col_of(0), v[0]);
 #pragma unroll 1
       for (int i = 0; i < NCH; i += 2) {  // ping-pong (rolled: keeps the epilogue inside the instruction cache)
         if (i < n_mine) {
           const long long t0 = TIC();
           tc_wait_ld();
           TOC(3, t0);
-          if (i + 1 < n_mine) tmem_ld16(tmem + lane_base + col_of(i + 1), v[1]);
+          if (i + 1 < n_mine) E1_LD(tmem + lane_base + col_of(i + 1), v[1]);
           chunk(v[0], col_of(i));
         }
         if (i + 1 < n_mine) {
           const long long t0 = TIC();
           tc_wait_ld();
           TOC(3, t0);
-          if (i + 2 < n_mine) tmem_ld16(tmem + lane_base + col_of(i + 2), v[0]);
+          if (i + 2 < n_mine) E1_LD(tmem + lane_base + col_of(i + 2), v[0]);
           chunk(v[1], col_of(i + 1));
         }
       }
