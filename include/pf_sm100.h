@@ -140,6 +140,24 @@ long long pf_format_phylip(const float* dm_host, int n, const char* const* names
 long long pf_neighbor_joining(const float* dm_host, int n, const char* const* names, char* out,
                               long long cap);
 
+/* Replaces the tree step of the reference's workflow (README.md:85-92: `fastme -i x.phy -o x.nwk --nni --spr`,
+ * FastME 2.1.6.4, shipped only as bin/bin_linux/fastme): host-only.  BIONJ start tree (PF_TREE_NJ_START: plain
+ * NJ), then a balanced-minimum-evolution search by NNIs (PF_TREE_NNI) and one by SPRs (PF_TREE_SPR), both from
+ * the start tree, best improvement first.  Output rule as observed on the binary: without a search the start
+ * tree with its own (BIONJ) branch lengths; with a search the shortest of { start tree with its own BIONJ branch
+ * lengths, NNI result, SPR result }.  dm_host is the symmetric (n,n) matrix in DOUBLE precision (what FastME
+ * parses from the "%.10f" PHYLIP text); Newick with "%.8f" branch lengths (FastME's default digits, negative
+ * lengths kept) into out[0..cap).  stats (optional, 7 doubles): length of the start tree with its own branch
+ * lengths, balanced length of the start tree, after NNI, after SPR, number of NNIs, number of SPRs, which tree
+ * was kept (0 start, 1 NNI, 2 SPR).  Returns the text length (call again with a larger buffer if it exceeds
+ * cap), or a negative PF_ERR_*.  n <= PF_BME_MAX_TAXA. */
+#define PF_TREE_NNI 1
+#define PF_TREE_SPR 2
+#define PF_TREE_NJ_START 4
+#define PF_BME_MAX_TAXA 2000
+long long pf_bme_tree(const double* dm_host, int n, const char* const* names, int flags, char* out,
+                      long long cap, double* stats);
+
 /* Kernel launches enqueued by the last pf_forward on this handle (for bench.py's
  * gpu_launches claim). */
 int pf_last_launch_count(pf_handle h);

@@ -93,6 +93,9 @@ def main(argv=None):
     parser.add_argument("--outdir", "-o", default=None, required=False,
                         help="Path to directory where inferred distance matrices will be written")
     parser.add_argument("--trees", "-t", action="store_true", help="Output NJ trees as well as matrices")
+    parser.add_argument("--bme-trees", "-b", action="store_true",
+                        help="Also output <stem>.bme.nwk: BIONJ + balanced NNI/SPR trees, what the README's "
+                             "`fastme -i <stem>.phy --nni --spr` step builds (not a reference option)")
     args = parser.parse_args(argv)
 
     nj = None
@@ -104,6 +107,10 @@ def main(argv=None):
         except ImportError:
             from phyloformer_b200.nj import neighbor_joining_c
             nj = lambda dm, ids: neighbor_joining_c(dm, ids) + "\n"        # noqa: E731
+    bme = None
+    if args.bme_trees:
+        from phyloformer_b200.bme import bme_tree
+        bme = lambda dm, ids: bme_tree(np.round(dm, 10), ids) + "\n"   # noqa: E731  (the '%.10f' values of the .phy text)
     if not torch.cuda.is_available():
         raise RuntimeError("infer_alns.py (B200 build) needs a CUDA device; there is no CPU fallback")
     if args.outdir is None:
@@ -121,11 +128,11 @@ def main(argv=None):
             raise ValueError("Input files must be fasta files (.fa or .fasta). Got " f"{alnpath}")
     max_tokens = float(os.environ.get("PF_MAX_BATCH_TOKENS", 2e7))
     with torch.no_grad(), tqdm(total=len(paths)) as bar:
-        run_pipeline(model, paths, out_dir, nj, max_tokens, bar.update)
+        run_pipeline(model, paths, out_dir, nj, max_tokens, bar.update, bme=bme)
 
 
-def write_outputs(out_dir, chunk, mats, nj):
-    """Host-side tail for one batched call: PHYLIP text (and optionally the NJ tree) per file."""
+def write_outputs(out_dir, chunk, mats, nj, bme=None):
+    """Host-side tail for one batched call: PHYLIP text (and optionally the NJ / BME tree) per file."""
     for (alnpath, _, ids), dm in zip(chunk, mats):
         stem = Path(alnpath).stem
         with open(os.path.join(out_dir, f"{stem}.phy"), "w") as outfile:
@@ -133,13 +140,16 @@ def write_outputs(out_dir, chunk, mats, nj):
         if nj is not None:
             with open(os.path.join(out_dir, f"{stem}.nj.nwk"), "w") as outfile:
                 outfile.write(nj(dm.astype(np.float64), ids))
+        if bme is not None:
+            with open(os.path.join(out_dir, f"{stem}.bme.nwk"), "w") as outfile:
+                outfile.write(bme(dm.astype(np.float64), ids))
     return len(chunk)
 
 
 MAX_BATCH = 65535  # alignments per batched call: the batch index is a gridDim.y/z of several kernels
 
 
-def run_pipeline(model, paths, out_dir, nj, max_tokens, progress=lambda k: None, depth=2):
+def run_pipeline(model, paths, out_dir, nj, max_tokens, progress=lambda k: None, depth=2, bme=None):
     """Three overlapped stages (the reference does them serially per file, infer_alns.py:97-117):
 
       parse        FASTA -> (n, L) uint8 codes (C parser), on the submitting thread while the
@@ -174,7 +184,7 @@ def run_pipeline(model, paths, out_dir, nj, max_tokens, progress=lambda k: None,
     def retire(pool):
         chunk, _stage, mats, done = inflight.popleft()
         done.synchronize()
-        writes.append(pool.submit(write_outputs, out_dir, chunk, mats.numpy(), nj))
+        writes.append(pool.submit(write_outputs, out_dir, chunk, mats.numpy(), nj, bme))
 
     # Parsing stays on this thread: it is one C pass per file (pf_parse_fasta, ~40 us for 20 x 200)
     # and every device call below is asynchronous, so the GPU works on batch k while this loop

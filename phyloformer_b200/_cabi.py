@@ -43,6 +43,7 @@ SYMBOLS = {
                                            c_void_p, c_void_p, c_int32, POINTER(c_int32)]),
     "pf_format_phylip": (ctypes.c_longlong, [c_void_p, c_int, POINTER(c_char_p), c_char_p, ctypes.c_longlong]),
     "pf_neighbor_joining": (ctypes.c_longlong, [c_void_p, c_int, POINTER(c_char_p), c_char_p, ctypes.c_longlong]),
+    "pf_bme_tree": (ctypes.c_longlong, [c_void_p, c_int, POINTER(c_char_p), c_int, c_char_p, ctypes.c_longlong, c_void_p]),
     "pf_last_launch_count": (c_int, [c_void_p]),
     "pf_set_peer_exchange": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p), c_size_t]),
     "pf_peer_exchange_bytes": (c_size_t, [c_size_t]),

@@ -18,6 +18,7 @@
 #include "pf_ffn_tc.cuh"
 #include "pf_ffn_ws.cuh"
 #include "pf_attn_tc.cuh"
+#include "pf_bme.h"
 
 namespace {
 
@@ -798,6 +799,15 @@ long long pf_format_phylip(const float* dm_host, int n, const char* const* names
   return pos;   // bytes of text; the caller retries with a larger buffer if this exceeds cap
 }
 
+// Newick label: names holding blanks or Newick punctuation are single-quoted, embedded quotes doubled (nj.py: newick_label)
+static std::string newick_label(const char* s) {
+  std::string v(s);
+  if (!v.empty() && v.find_first_of(" \t\r\n,:;()[]'") == std::string::npos) return v;
+  std::string q = "'";
+  for (char c : v) { q += c; if (c == '\'') q += c; }
+  return q + "'";
+}
+
 // ---- host-side neighbour joining (no device work) ---------------------------------------------
 // Saitou & Nei / Studier & Keppler, O(n^3) in double precision; same joins, tie-breaking (first
 // minimum of Q in row-major order) and Newick layout as phyloformer_b200/nj.py.
@@ -811,14 +821,7 @@ long long pf_neighbor_joining(const float* dm_host, int n, const char* const* na
     snprintf(b, sizeof(b), "%.10f", x);
     return std::string(b);
   };
-  // Newick label: names holding blanks or Newick punctuation are single-quoted, embedded quotes doubled (nj.py: newick_label)
-  auto label = [](const char* s) {
-    std::string v(s);
-    if (!v.empty() && v.find_first_of(" \t\r\n,:;()[]'") == std::string::npos) return v;
-    std::string q = "'";
-    for (char c : v) { q += c; if (c == '\'') q += c; }
-    return q + "'";
-  };
+  auto label = [](const char* s) { return newick_label(s); };
   std::string tree;
   try {
   if (n == 1) {
@@ -871,6 +874,34 @@ long long pf_neighbor_joining(const float* dm_host, int n, const char* const* na
   }
   } catch (...) {   // nothing may propagate across the C ABI
     return (long long)fail(PF_ERR_ARG, "pf_neighbor_joining: out of host memory (n = %d)", n);
+  }
+  const long long len = (long long)tree.size();
+  if (len <= cap) memcpy(out, tree.data(), (size_t)len);
+  return len;
+}
+
+// ---- host-side BIONJ + balanced NNI / SPR tree search (no device work; pf_bme.h) -----------------
+long long pf_bme_tree(const double* dm_host, int n, const char* const* names, int flags, char* out, long long cap,
+                      double* stats) {
+  if (!dm_host || !names || n < 1 || (cap > 0 && !out)) return (long long)fail(PF_ERR_ARG, "pf_bme_tree: bad argument");
+  if (n > PF_BME_MAX_TAXA)
+    return (long long)fail(PF_ERR_ARG, "pf_bme_tree: %d taxa exceed the limit of %d (the table of subtree averages grows with n^2)", n, PF_BME_MAX_TAXA);
+  for (int i = 0; i < n; ++i)
+    if (!names[i]) return (long long)fail(PF_ERR_ARG, "pf_bme_tree: null name %d", i);
+  for (size_t i = 0; i < (size_t)n * n; ++i)
+    if (!std::isfinite(dm_host[i])) return (long long)fail(PF_ERR_ARG, "pf_bme_tree: non-finite distance at element %zu", i);
+  std::string tree;
+  try {
+    std::vector<std::string> labels((size_t)n);
+    for (int i = 0; i < n; ++i) labels[i] = newick_label(names[i]);
+    const pfbme::Result r = pfbme::build(dm_host, n, labels, flags);
+    tree = r.newick;
+    if (stats) {
+      stats[0] = r.length_own; stats[1] = r.length_start; stats[2] = r.length_nni; stats[3] = r.length_spr;
+      stats[4] = r.n_nni; stats[5] = r.n_spr; stats[6] = r.kept;
+    }
+  } catch (...) {   // nothing may propagate across the C ABI
+    return (long long)fail(PF_ERR_ARG, "pf_bme_tree: out of host memory (n = %d)", n);
   }
   const long long len = (long long)tree.size();
   if (len <= cap) memcpy(out, tree.data(), (size_t)len);

@@ -16,6 +16,7 @@
 // two child subtrees' averages (every split halves the weight, whatever the subtree sizes).
 #pragma once
 
+#include <algorithm>
 #include <array>
 #include <cmath>
 #include <cstdint>
@@ -51,38 +52,67 @@ struct Tree {
   }
 };
 
-// Balanced averages between disjoint subtrees of the current topology, filled on demand.
+// Balanced averages between all pairs of disjoint subtrees of the current topology: one H x H table
+// (H directed edges), rebuilt after every accepted move.  Directed edges are visited by increasing subtree
+// size, so a row is the mean of its two child rows (one contiguous pass per row); rows of leaf-pointing edges
+// are filled along the same order from the distance matrix.  Entries of overlapping subtrees are meaningless
+// and never read.
 struct Averages {
   const Tree& t;
   const double* D;
   int H;
   std::vector<double> val;
-  std::vector<uint8_t> done;
+  std::vector<int> c1, c2, order;
   Averages(const Tree& tree, const double* dist) : t(tree), D(dist), H(2 * tree.n_edges()) {
     val.resize((size_t)H * H);
-    done.assign((size_t)H * H, 0);
+    c1.resize((size_t)H); c2.resize((size_t)H); order.resize((size_t)H);
+    fill();
   }
-  void reset() { std::fill(done.begin(), done.end(), (uint8_t)0); }
-  double get(int a, int b) {
-    const size_t i = (size_t)a * H + b;
-    if (done[i]) return val[i];
-    const int wa = t.head(a), wb = t.head(b);
-    double v;
-    if (wa < t.n && wb < t.n) {
-      v = D[(size_t)wa * t.n + wb];
-    } else if (wa >= t.n) {
-      int c1, c2;
-      t.children(a, c1, c2);
-      v = 0.5 * (get(c1, b) + get(c2, b));
-    } else {
-      int c1, c2;
-      t.children(b, c1, c2);
-      v = 0.5 * (get(a, c1) + get(a, c2));
+  void reset() { fill(); }
+  double get(int a, int b) const { return val[(size_t)a * H + b]; }
+  void fill() {
+    if (H == 0) return;
+    const int n = t.n;
+    // subtree sizes: depth-first from leaf 0; (parent -> v) holds the leaves below v, (v -> parent) the rest
+    std::vector<int> size((size_t)H, 0), stack, parent_edge((size_t)t.n_nodes(), -1), seq;
+    stack.push_back(0);
+    while (!stack.empty()) {
+      const int v = stack.back();
+      stack.pop_back();
+      seq.push_back(v);
+      for (int k = 0; k < 3; ++k) {
+        const int e = t.adj[v][k];
+        if (e < 0 || e == parent_edge[v]) continue;
+        const int w = (t.ends[e][0] == v) ? t.ends[e][1] : t.ends[e][0];
+        parent_edge[w] = e;
+        stack.push_back(w);
+      }
     }
-    val[i] = v; done[i] = 1;
-    const size_t j = (size_t)b * H + a;
-    val[j] = v; done[j] = 1;
-    return v;
+    std::vector<int> below((size_t)t.n_nodes(), 0);
+    for (size_t q = seq.size(); q-- > 1;) {       // children before parents
+      const int v = seq[q], e = parent_edge[v];
+      if (v < n) below[v] = 1;
+      const int par = (t.ends[e][0] == v) ? t.ends[e][1] : t.ends[e][0];
+      below[par] += below[v];
+      size[t.dir(par, e)] = below[v];
+      size[t.dir(v, e)] = n - below[v];
+    }
+    for (int h = 0; h < H; ++h) {
+      order[h] = h;
+      if (t.head(h) >= n) t.children(h, c1[h], c2[h]); else c1[h] = c2[h] = -1;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return size[a] < size[b]; });
+    for (int a : order) {
+      double* row = &val[(size_t)a * H];
+      if (c1[a] < 0) {
+        const double* drow = D + (size_t)t.head(a) * n;
+        for (int b : order) row[b] = (c1[b] < 0) ? drow[t.head(b)] : 0.5 * (row[c1[b]] + row[c2[b]]);
+      } else {
+        const double* r1 = &val[(size_t)c1[a] * H];
+        const double* r2 = &val[(size_t)c2[a] * H];
+        for (int b = 0; b < H; ++b) row[b] = 0.5 * (r1[b] + r2[b]);
+      }
+    }
   }
 };
 
@@ -113,9 +143,11 @@ inline double tree_length(const Tree& t, Averages& A) {
 // reduction d_uk = lambda (d_ik - l_i) + (1 - lambda)(d_jk - l_j); the first minimum in the scan order
 // x = 0..n-1, y < x wins and a later pair must beat it by more than 1e-6 (the published implementation's
 // tie rule).  The new cluster takes the slot of x.  With bionj = false lambda is 1/2 (plain NJ).
-inline Tree bionj(const double* D, int n, bool use_bionj = true) {
+inline Tree bionj(const double* D, int n, bool use_bionj = true, std::vector<double>* own_lengths = nullptr) {
   Tree t;
+  std::vector<double> blen;   // the agglomeration's own branch lengths, per edge
   t.n = n;
+  if (n < 2) return t;      // a single taxon: no edges
   t.adj.assign((size_t)(2 * n - 2), {-1, -1, -1});
   t.ends.reserve((size_t)(2 * n - 3));
   auto connect = [&](int a, int b) {
@@ -125,7 +157,11 @@ inline Tree bionj(const double* D, int n, bool use_bionj = true) {
       for (int s = 0; s < 3; ++s)
         if (t.adj[node][s] < 0) { t.adj[node][s] = e; break; }
   };
-  if (n == 2) { connect(0, 1); return t; }
+  if (n == 2) {
+    connect(0, 1);
+    if (own_lengths) own_lengths->assign(1, D[1]);
+    return t;
+  }
   std::vector<double> d((size_t)n * n), var((size_t)n * n), S((size_t)n);
   for (size_t i = 0; i < (size_t)n * n; ++i) d[i] = var[i] = D[i];
   std::vector<int> node((size_t)n);      // tree node currently represented by slot i
@@ -172,15 +208,22 @@ inline Tree bionj(const double* D, int n, bool use_bionj = true) {
       vv(a, i) = vv(i, a) = vu;
     }
     const int u = next_node++;
-    connect(u, node[a]);
-    connect(u, node[b]);
+    connect(u, node[a]); blen.push_back(la);
+    connect(u, node[b]); blen.push_back(lb);
     node[a] = u;
     alive[b] = 0;
     --r;
   }
   const int u = next_node++;
+  int last[3], k = 0;
   for (int i = 0; i < n; ++i)
-    if (alive[i]) connect(u, node[i]);
+    if (alive[i]) last[k++] = i;
+  for (int m = 0; m < 3; ++m) {
+    const int i = last[m], j = last[(m + 1) % 3], l = last[(m + 2) % 3];
+    connect(u, node[i]);
+    blen.push_back(0.5 * (dd(i, j) + dd(i, l) - dd(j, l)));
+  }
+  if (own_lengths) *own_lengths = blen;
   return t;
 }
 
@@ -230,28 +273,25 @@ struct SprSearch {
   Averages A;
   double best;
   int best_s, best_target;
-  std::vector<int> comp;       // subtrees (directed edges) that make up `behind`
-  std::vector<double> wgt;     // their weights
   SprSearch(Tree& tree, const double* D) : t(tree), A(tree, D), best(0), best_s(-1), best_target(-1) {}
-  double behind_avg(int x) {
-    double s = 0.0;
-    for (size_t i = 0; i < comp.size(); ++i) s += wgt[i] * A.get(comp[i], x);
-    return s;
-  }
-  void walk(int s, int r, double cum) {   // S is about to cross head(r)
+  // S (directed edge s, first neighbour subtree a0) is about to cross head(r) after k earlier crossings.
+  // `behind` = a0 joined with the side subtrees passed so far; together with S it is the subtree U of r
+  // reversed in the unmodified tree, where S carries the weight a0 has in `behind`:
+  //   avg(behind, X) = avg(U, X) - 2^-(k+1) (avg(S, X) - avg(a0, X)),
+  // and avg(behind, S) follows the crossings: bs <- (bs + avg(B, S)) / 2.
+  void walk(int s, int a0, int r, double cum, double scale, double bs) {
     if (t.head(r) < t.n) return;
-    int z[2];
-    t.children(r, z[0], z[1]);
-    const double bs = behind_avg(s);
+    const int z[2] = {A.c1[r], A.c2[r]};
+    const double* row_s = &A.val[(size_t)s * A.H];
+    const double* row_a = &A.val[(size_t)a0 * A.H];
+    const double* row_u = &A.val[(size_t)(r ^ 1) * A.H];
+    const double bb = A.get(z[0], z[1]);
     for (int k = 0; k < 2; ++k) {
       const int R = z[k], B = z[k ^ 1];
-      const double delta = cum + 0.25 * (behind_avg(B) + A.get(s, R) - bs - A.get(B, R));
+      const double behind_b = row_u[B] - scale * (row_s[B] - row_a[B]);
+      const double delta = cum + 0.25 * (behind_b + row_s[R] - bs - bb);
       if (delta < best) { best = delta; best_s = s; best_target = R >> 1; }
-      for (double& w : wgt) w *= 0.5;
-      comp.push_back(B); wgt.push_back(0.5);
-      walk(s, R, delta);
-      comp.pop_back(); wgt.pop_back();
-      for (double& w : wgt) w *= 2.0;
+      walk(s, a0, R, delta, 0.5 * scale, 0.5 * (bs + row_s[B]));
     }
   }
   void scan(double eps) {
@@ -259,12 +299,9 @@ struct SprSearch {
     for (int s = 0; s < 2 * t.n_edges(); ++s) {
       const int p = t.tail(s);
       if (p < t.n) continue;                 // a subtree is pruned from an internal vertex
-      int x, y;
-      t.children(s ^ 1, x, y);               // the two other directed edges leaving p
-      comp.assign(1, y); wgt.assign(1, 1.0);
-      walk(s, x, 0.0);
-      comp.assign(1, x); wgt.assign(1, 1.0);
-      walk(s, y, 0.0);
+      const int x = A.c1[s ^ 1], y = A.c2[s ^ 1];   // the two other directed edges leaving p
+      walk(s, y, x, 0.0, 0.5, A.get(y, s));
+      walk(s, x, y, 0.0, 0.5, A.get(x, s));
     }
   }
   void apply() {   // move p (with S attached) into the middle of the target edge
@@ -302,8 +339,9 @@ inline int bme_spr(Tree& t, const double* D, double eps, int max_moves = 1 << 30
 
 // Newick text rooted at the last internal node (trifurcation), balanced branch lengths.
 inline std::string newick(const Tree& t, const double* D, const std::vector<std::string>& labels, int digits,
-                          bool clip_negative) {
+                          bool clip_negative, const std::vector<double>* lengths = nullptr) {
   Averages A(t, D);
+  auto edge_len = [&](int e) { return lengths ? (*lengths)[(size_t)e] : edge_length(t, A, e); };
   auto fmt = [&](double x) {
     char b[420];
     if (clip_negative && x < 0) x = 0.0;
@@ -324,7 +362,7 @@ inline std::string newick(const Tree& t, const double* D, const std::vector<std:
   while (!st.empty()) {
     Frame& f = st.back();
     if (f.node < t.n) {
-      std::string leaf = labels[f.node] + ":" + fmt(edge_length(t, A, f.via));
+      std::string leaf = labels[f.node] + ":" + fmt(edge_len(f.via));
       st.pop_back();
       Frame& par = st.back();
       if (par.text.size() > 1) par.text += ",";
@@ -339,7 +377,7 @@ inline std::string newick(const Tree& t, const double* D, const std::vector<std:
       continue;
     }
     std::string done = f.text + ")";
-    if (f.via >= 0) done += ":" + fmt(edge_length(t, A, f.via));
+    if (f.via >= 0) done += ":" + fmt(edge_len(f.via));
     st.pop_back();
     if (st.empty()) { result = done + ";"; break; }
     Frame& par = st.back();
@@ -351,38 +389,53 @@ inline std::string newick(const Tree& t, const double* D, const std::vector<std:
 
 struct Result {
   std::string newick;
-  double length_start, length_nni, length_spr;
+  double length_own;     // start tree with the agglomeration's own branch lengths
+  double length_start;   // start tree, balanced lengths (what the searches start from)
+  double length_nni, length_spr;
   int n_nni, n_spr;
-  bool kept_spr;
+  int kept;              // 0 start tree, 1 NNI result, 2 SPR result
 };
 
 // flags: bit 0 = NNI search, bit 1 = SPR search, bit 2 = plain NJ start tree instead of BIONJ.
+// Without a search the start tree is written with the agglomeration's own branch lengths (`fastme -i x` alone).
+// With a search, FastME keeps the shortest of { start tree with its own (BIONJ) branch lengths, NNI result, SPR result };
+// observed on the binary: whenever the BIONJ length is below both balanced lengths the output is the BIONJ tree
+// with BIONJ branch lengths (tools/bme_vs_fastme.py).
 inline Result build(const double* D, int n, const std::vector<std::string>& labels, int flags, int digits = 8,
                     bool clip_negative = false, double eps = 1e-9) {
   Result r{};
-  Tree start = bionj(D, n, !(flags & 4));
-  Tree t_nni = start;
+  std::vector<double> own;
+  Tree start = bionj(D, n, !(flags & 4), &own);
+  for (double x : own) r.length_own += x;
   {
     Averages A(start, D);
     r.length_start = (n >= 2) ? tree_length(start, A) : 0.0;
   }
   r.length_nni = r.length_spr = r.length_start;
+  if (!(flags & 3) || n < 4) {
+    r.newick = newick(start, D, labels, digits, clip_negative, &own);
+    return r;
+  }
+  const Tree* out = &start;
+  double best = r.length_own;
+  Tree t_nni, t_spr;
   if (flags & 1) {
+    t_nni = start;
     r.n_nni = bme_nni(t_nni, D, eps);
     Averages A(t_nni, D);
     r.length_nni = tree_length(t_nni, A);
+    // (FastME's BIONJ length carries single-precision noise of ~1e-8; on four taxa, where both lengths are equal in
+    //  exact arithmetic, the binary ends on the balanced tree: a tie goes to the search result)
+    if (r.length_nni < best + 1e-7) { best = std::min(best, r.length_nni); out = &t_nni; r.kept = 1; }
   }
-  const Tree* out = &t_nni;
-  Tree t_spr;
   if (flags & 2) {
     t_spr = start;
     r.n_spr = bme_spr(t_spr, D, eps);
     Averages A(t_spr, D);
     r.length_spr = tree_length(t_spr, A);
-    // two searches from the same start tree, the shorter result wins (FastME's rule when both are asked for)
-    if (!(flags & 1) || r.length_spr < r.length_nni - eps) { out = &t_spr; r.kept_spr = true; }
+    if (r.length_spr < best + (r.kept == 0 ? 1e-7 : 0.0)) { best = std::min(best, r.length_spr); out = &t_spr; r.kept = 2; }
   }
-  r.newick = newick(*out, D, labels, digits, clip_negative);
+  r.newick = newick(*out, D, labels, digits, clip_negative, r.kept == 0 ? &own : nullptr);
   return r;
 }
 

@@ -9,7 +9,9 @@ Gate: collapsed RF == 0 everywhere; strict RF == 0 on every alignment in fp32 mo
 known self-inconsistent one.
 
 FastME is a third-party binary: tools/stage_ref.sh copies it to baseline/_ref/bin (git-ignored,
-travels with the gpurun snapshot).  Skipped if it is absent."""
+travels with the gpurun snapshot).  The FastME test is skipped if it is absent; the second test builds the
+trees with the library's own BIONJ + balanced NNI / SPR search (pf_bme_tree, pinned on FastME's outputs by
+tests/test_bme_cpu.py) and always runs."""
 import json
 import os
 import subprocess
@@ -51,3 +53,38 @@ def test_fastme_topologies_match_reference(tmp_path, prec):
     assert all(v == 0 for v in collapsed.values()), collapsed
     n_strict = sum(1 for v in strict.values() if v)
     assert n_strict <= (1 if prec == "fp32" else 3), strict
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+def test_own_bme_trees_match_reference(tmp_path, prec):
+    """The same gate without the external binary: distances from the GPU path -> '%.10f' PHYLIP values ->
+    pf_bme_tree (`infer_alns.py --bme-trees`), against the reference's FastME trees.  When the FastME binary is
+    staged, also tree for tree against FastME run on the very same PHYLIP text."""
+    import infer_alns
+    import numpy as np
+    from phyloformer.data import load_alignment_idx
+    from phyloformer_b200.bme import bme_tree, phylip_rounded
+    model = infer_alns.load_model(os.path.join(GOLDEN, "ckpt_pf.pt"), "cuda")
+    model.set_precision(prec)
+    ref_trees = json.load(open(os.path.join(GOLDEN, "ref_trees_pf.json")))
+    strict, collapsed, vs_binary = {}, {}, {}
+    for stem in list_stems():
+        idx, ids = load_alignment_idx(os.path.join(GOLDEN, "msas", stem + ".fa"))
+        with torch.no_grad():
+            d = model.forward_idx(idx.cuda())
+        dm, phy = infer_alns.vec_to_phylip(d, ids, model)
+        ours = bme_tree(phylip_rounded(np.asarray(dm.cpu(), dtype=np.float64)), ids)
+        strict[stem] = rf_distance(ours, ref_trees[stem])
+        collapsed[stem] = rf_distance(ours, ref_trees[stem], min_length=1e-8)
+        if os.path.exists(FASTME):
+            p = tmp_path / f"{stem}.phy"
+            p.write_text(phy)
+            subprocess.run([FASTME, "-i", str(p), "-o", str(p) + ".nwk", "--nni", "--spr"], check=True,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=tmp_path)
+            vs_binary[stem] = rf_distance(ours, open(str(p) + ".nwk").read().strip(), min_length=1e-8)
+    print(f"[{prec}, pf_bme_tree] strict RF != 0: { {k: v for k, v in strict.items() if v} }  collapsed RF != 0: "
+          f"{ {k: v for k, v in collapsed.items() if v} }  vs the FastME binary on the same text (collapsed): "
+          f"{ {k: v for k, v in vs_binary.items() if v} }")
+    assert all(v == 0 for v in collapsed.values()), collapsed
+    assert all(v == 0 for v in vs_binary.values()), vs_binary
+    assert sum(1 for v in strict.values() if v) <= (1 if prec == "fp32" else 3), strict
