@@ -5,8 +5,8 @@ matrices (README.md:85-92: `fastme -i X.phy -o X.nwk --nni --spr`).
 Reported per SURVEY 7.4.2: strict RF and RF after collapsing internal branches <= 1e-8 (13/20
 alignments contain duplicate sequences whose zero-length branches FastME resolves by fp noise;
 the reference disagrees with itself on the strict gate for 1_40_tips between 1 and 8 threads).
-Gate: collapsed RF == 0 everywhere; strict RF == 0 on every alignment in fp32 mode except the
-known self-inconsistent one.
+Gate: collapsed RF == 0 everywhere; strict RF == 0 on every alignment, in both precision modes, except the
+known self-inconsistent one (the kernels are deterministic, so the gate does not flicker).
 
 FastME is a third-party binary: tools/stage_ref.sh copies it to baseline/_ref/bin (git-ignored,
 travels with the gpurun snapshot).  The FastME test is skipped if it is absent; the second test builds the
@@ -24,6 +24,8 @@ from tests._util import GOLDEN, ROOT, list_stems
 
 pytestmark = pytest.mark.gpu
 FASTME = os.path.join(ROOT, "baseline", "_ref", "bin", "fastme")
+# five identical sequences: the reference's own 1-thread and 8-thread matrices give different strict topologies here
+SELF_INCONSISTENT = {"1_40_tips"}
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
@@ -51,8 +53,7 @@ def test_fastme_topologies_match_reference(tmp_path, prec):
     print(f"[{prec}] strict RF != 0: { {k: v for k, v in strict.items() if v} }  collapsed RF != 0: "
           f"{ {k: v for k, v in collapsed.items() if v} }")
     assert all(v == 0 for v in collapsed.values()), collapsed
-    n_strict = sum(1 for v in strict.values() if v)
-    assert n_strict <= (1 if prec == "fp32" else 3), strict
+    assert {k for k, v in strict.items() if v} <= SELF_INCONSISTENT, strict
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
@@ -87,4 +88,4 @@ def test_own_bme_trees_match_reference(tmp_path, prec):
           f"{ {k: v for k, v in vs_binary.items() if v} }")
     assert all(v == 0 for v in collapsed.values()), collapsed
     assert all(v == 0 for v in vs_binary.values()), vs_binary
-    assert sum(1 for v in strict.values() if v) <= (1 if prec == "fp32" else 3), strict
+    assert {k for k, v in strict.items() if v} <= SELF_INCONSISTENT, strict
