@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpf_sm100.so")
 SOURCES = ["pf_api.cu"]
-HEADERS = ["pf_common.cuh", "pf_kernels.cuh", "pf_ffn_tc.cuh", "pf_ffn_ws.cuh", "pf_attn_tc.cuh", os.path.join("..", "..", "include", "pf_sm100.h")]
+HEADERS = ["pf_common.cuh", "pf_kernels.cuh", "pf_ffn_tc.cuh", "pf_ffn_ws.cuh", "pf_attn_tc.cuh", "pf_bme.h", os.path.join("..", "..", "include", "pf_sm100.h")]
 
 
 def _nvcc():

@@ -47,6 +47,9 @@
 // took: the work per SM is conserved whichever warps do it (TMEM / MIO path, not warp latency).
 // 16 epilogue warps at <= 80 registers with a row-chunked producer (x2 staged through TMEM, 12 extra TMEM
 // instructions per row): built and measured in round 2, 34.7 vs 32.5 ms of FFN time per forward -> removed.
+// Final-row stores (E2) after E1b instead of between E1a and E1b -- for column group 1 only (so that on every scheduler
+// one epilogue warp waits on TMEM / stores while the other runs GELU) or for both groups (E2 off the E1a -> E1b -> G2b
+// path): parity green, FFN time per forward 29.9 / 31.0 vs 28.97 ms (same box, back to back) -> removed.
 // WS_B1_CONST = 1: the epilogue reads b1 through the constant bank (LDC) instead of shared memory, whose loads queue
 // behind the previous chunk's tcgen05.st in the MIO queue
 #ifdef WS_DIAG_NO_LDTM   // timing diagnostic only (wrong results): no TMEM reads in E1
