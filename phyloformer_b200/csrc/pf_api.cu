@@ -95,6 +95,7 @@ struct pf_ctx {
   PfBlockW* blk_dev = nullptr;  // [nb]
   PfFfnTcW* tc_dev = nullptr;   // [nb] bf16 hi/lo smem images for the tcgen05 FFN
   PfFfnTcW* tc16_dev = nullptr; // [nb] the same in fp16 (PF_PREC_FP16)
+  PfFfnTcW* tcf_dev = nullptr;  // [nb] bf16 hi/lo images with the first bias folded into W1 (WS_FOLD63: k_colapply_ffn_ws, parity format)
   PfAttnTcW* atc_dev = nullptr; // [nb][2] q/k weight images for the tcgen05 attention kernels (0: row, 1: column)
   int col_impl = 2;             // 0: k_col_partial (FFMA), 1: k_col_partial_tc (tcgen05, one thread per token),
                                 // 2: k_col_partial_ws (tcgen05, warp specialised); env PF_COL_IMPL=cc|tc1|tc
@@ -315,7 +316,7 @@ int pf_create(pf_handle* out, const pf_cfg* cfg, const float* const* weights_dev
     head[0].bhead = hw.t[hb + 1][0];
   }
   std::vector<PfBlockW> blk(nb);
-  std::vector<PfFfnTcW> tc(nb), tc16(nb);
+  std::vector<PfFfnTcW> tc(nb), tc16(nb), tcf(nb);
   std::vector<PfAttnTcW> atc(2 * nb);
   for (int b = 0; b < nb; ++b) {
     const int base = 2 + 26 * b;
@@ -324,6 +325,7 @@ int pf_create(pf_handle* out, const pf_cfg* cfg, const float* const* weights_dev
     pack_ffn(hw, base + 22, base + 20, &blk[b].ffn);
     pf_pack_ffn_tc(blk[b].ffn, &tc[b]);
     pf_pack_ffn_tc(blk[b].ffn, &tc16[b], true);
+    pf_pack_ffn_tc(blk[b].ffn, &tcf[b], false, true);
     pf_pack_attn_tc(blk[b].row, &atc[2 * b]);
     pf_pack_attn_tc(blk[b].col, &atc[2 * b + 1]);
     PfFfnConst kc;
@@ -364,6 +366,8 @@ int pf_create(pf_handle* out, const pf_cfg* cfg, const float* const* weights_dev
       (e = cudaMalloc(&h->blk_dev, sizeof(PfBlockW) * nb)) != cudaSuccess ||
       (e = cudaMalloc(&h->tc_dev, sizeof(PfFfnTcW) * nb)) != cudaSuccess ||
       (e = cudaMalloc(&h->tc16_dev, sizeof(PfFfnTcW) * nb)) != cudaSuccess ||
+      (e = cudaMalloc(&h->tcf_dev, sizeof(PfFfnTcW) * nb)) != cudaSuccess ||
+      (e = cudaMemcpy(h->tcf_dev, tcf.data(), sizeof(PfFfnTcW) * nb, cudaMemcpyHostToDevice)) != cudaSuccess ||
       (e = cudaMalloc(&h->atc_dev, sizeof(PfAttnTcW) * 2 * nb)) != cudaSuccess ||
       (e = cudaMemcpy(h->atc_dev, atc.data(), sizeof(PfAttnTcW) * 2 * nb, cudaMemcpyHostToDevice)) != cudaSuccess ||
       (e = cudaMalloc(&h->row0_dev, sizeof(Row0Tab))) != cudaSuccess ||
@@ -419,6 +423,7 @@ void pf_destroy(pf_handle h) {
   if (h->blk_dev) cudaFree(h->blk_dev);
   if (h->tc_dev) cudaFree(h->tc_dev);
   if (h->tc16_dev) cudaFree(h->tc16_dev);
+  if (h->tcf_dev) cudaFree(h->tcf_dev);
   if (h->atc_dev) cudaFree(h->atc_dev);
   if (h->err_dev) cudaFree(h->err_dev);
   if (h->row0_dev) cudaFree(h->row0_dev);
@@ -649,7 +654,9 @@ int pf_forward_debug(pf_handle h, const uint8_t* msa_idx_dev, const float* x_dev
       if (prec == PF_PREC_FP16 && h->ffn_impl != 1)
         return fail(PF_ERR_ARG, "pf_forward: PF_PREC_FP16 needs the warp-specialised FFN kernel (unset PF_FFN_IMPL)");
       const int rc = h->ffn_impl == 1
-                         ? pf_ffn_ws_launch(h->ffn_const[b], (prec == PF_PREC_FP16 ? h->tc16_dev : h->tc_dev) + b, x, colM,
+                         ? pf_ffn_ws_launch(h->ffn_const[b],
+                                            (WS_FOLD63 && fmt == WS_FMT_BF16X3) ? h->tcf_dev + b
+                                                      : (prec == PF_PREC_FP16 ? h->tc16_dev : h->tc_dev) + b, x, colM,
                                             col_tc ? qcache : nullptr, L,
                                             (int)pl.Pl, B, h->n_sm, fmt, terms, h->err_dev, h->dump_dev, h->ws_prof, st,
                                             fuse_head ? headpart : nullptr)

@@ -12,6 +12,19 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Suspend-time hint (ns) of every bounded mbarrier.try_wait in this library; PF_WAIT_HINT=0 builds the waits without a
+// hint (the hardware's own time limit per try).  A/B at the end of round 2: see profiles/r02_experiments.md.
+#ifndef PF_WAIT_HINT
+#define PF_WAIT_HINT 1000
+#endif
+#define PF_STR2(x) #x
+#define PF_STR(x) PF_STR2(x)
+#if PF_WAIT_HINT > 0
+#define PF_WAIT_HINT_STR ", " PF_STR(PF_WAIT_HINT)
+#else
+#define PF_WAIT_HINT_STR ""
+#endif
+
 #define PF_D 64
 #define PF_H 4
 #define PF_DH 16

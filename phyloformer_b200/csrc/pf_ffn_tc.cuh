@@ -74,14 +74,20 @@ inline float f16_to_f32(uint16_t u) {
 
 // Weight images for the tensor-core FFN: 16-bit hi/lo parts (bf16, or fp16 when `f16`), already in
 // the UMMA shared-memory layout.
-inline void pf_pack_ffn_tc(const PfFfnW& f, PfFfnTcW* o, bool f16 = false) {
+// fold63: the LayerNorm output sums to zero over its 64 channels, so channel 63 is redundant:
+//   sum_c W[n][c] u_c = sum_{c<63} (W[n][c] - W[n][63]) u_c.
+// The image then holds W[n][c] - W[n][63] in columns 0..62 and the bias b1[n] in column 63; the kernel writes the
+// constant 1 into operand column 63, the GEMM delivers W1 LN(x) + b1, and the epilogue has no bias to add (b1 = 0 here).
+inline void pf_pack_ffn_tc(const PfFfnW& f, PfFfnTcW* o, bool f16 = false, bool fold63 = false) {
   auto enc = [&](float w) { return f16 ? f32_to_f16_rn(w) : f32_to_bf16_rn(w); };
   auto dec = [&](uint16_t u) { return f16 ? f16_to_f32(u) : bf16_to_f32(u); };
   for (int n = 0; n < PF_HID; ++n)
     for (int k = 0; k < PF_D; ++k) {
-      const float w = f.w1T[k][n];
+      double wd = f.w1T[k][n];
+      if (fold63) wd = (k == PF_D - 1) ? (double)f.b1[n] : wd - (double)f.w1T[PF_D - 1][n];
+      const float w = (float)wd;
       const uint16_t hi = enc(w);
-      const uint16_t lo = enc(w - dec(hi));
+      const uint16_t lo = enc((float)(wd - (double)dec(hi)));
       const uint32_t off = umma_off_k64(n, k) / 2;
       o->w1hi[off] = hi;
       o->w1lo[off] = lo;
@@ -96,6 +102,7 @@ inline void pf_pack_ffn_tc(const PfFfnW& f, PfFfnTcW* o, bool f16 = false) {
       o->w2lo[off] = lo;
     }
   memcpy(o->b1, f.b1, sizeof(o->b1));
+  if (fold63) memset(o->b1, 0, sizeof(o->b1));
   memcpy(o->b2, f.b2, sizeof(o->b2));
 }
 
@@ -129,7 +136,7 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 1000;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2" PF_WAIT_HINT_STR ";\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(bar), "r"(parity)

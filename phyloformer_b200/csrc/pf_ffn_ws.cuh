@@ -63,6 +63,16 @@
 #ifndef WS_B1_CONST
 #define WS_B1_CONST 1
 #endif
+// WS_FOLD63 = 1: the first bias rides on GEMM1.  LN(x) sums to zero over its 64 channels, so operand column 63 is
+// redundant (pf_pack_ffn_tc folds its weight into the other 63 columns); the producer writes the constant 1 there and
+// the weight image carries b1 in that column: D1 = W1 LN(x) + b1 comes out of the tensor core and the epilogue saves the
+// bias load (LDC.64) and the packed add per pair of hidden units.  Needs the folded image (pf_handle::tcf_dev).
+// Parity format (bf16 hi/lo) only: with single-rounded operands the larger folded weights and the rounded bias cost
+// accuracy (fp16 mode 4.3e-3 -> 7.3e-3, bf16 mode 2.9e-2 -> 4.0e-2 max-rel on the 20 test alignments), so the fast
+// formats keep the unfolded images and the epilogue's bias add.
+#ifndef WS_FOLD63
+#define WS_FOLD63 1
+#endif
 #define WS_NCG (WS_EW / 4)            // epilogue column groups per TMEM lane quadrant
 #define WS_NPW 4                      // producer warps
 #define WS_PW0 WS_EW                  // first producer warp
@@ -415,7 +425,12 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const u64 nv = mul2(add2(pk2(xr[8 * ch + 2 * i], xr[8 * ch + 2 * i + 1]), nm), rs);
+            u64 nv = mul2(add2(pk2(xr[8 * ch + 2 * i], xr[8 * ch + 2 * i + 1]), nm), rs);
+            if (WS_FOLD63 && FMT == WS_FMT_BF16X3 && ch == 7 && i == 3) {   // operand column 63 carries the constant 1 (see WS_FOLD63)
+              float n62, n63;
+              up2(nv, n62, n63);
+              nv = pk2(n62, 1.0f);
+            }
             cvt2<FMT>(nv, hi[i], lo[i]);
           }
           const uint32_t off = rowoff + (uint32_t)(((ch ^ r) & 7) << 4);
@@ -530,8 +545,11 @@ k_colapply_ffn_ws(const __grid_constant__ PfFfnConst kc, const PfFfnTcW* __restr
 #if defined(WS_DIAG_NO_B1)
           up2(pk2(__uint_as_float(vc[2 * i]), __uint_as_float(vc[2 * i + 1])), h0, h1);
 #elif WS_B1_CONST
-          up2(add2(pk2(__uint_as_float(vc[2 * i]), __uint_as_float(vc[2 * i + 1])),
-                   pk2(kc.b1[cc + 2 * i], kc.b1[cc + 2 * i + 1])), h0, h1);
+          if (WS_FOLD63 && FMT == WS_FMT_BF16X3)   // the accumulator already holds W1 LN(x) + b1
+            up2(pk2(__uint_as_float(vc[2 * i]), __uint_as_float(vc[2 * i + 1])), h0, h1);
+          else
+            up2(add2(pk2(__uint_as_float(vc[2 * i]), __uint_as_float(vc[2 * i + 1])),
+                     pk2(kc.b1[cc + 2 * i], kc.b1[cc + 2 * i + 1])), h0, h1);
 #else
           up2(add2(pk2(__uint_as_float(vc[2 * i]), __uint_as_float(vc[2 * i + 1])),
                    *reinterpret_cast<const u64*>(sb1 + cc + 2 * i)), h0, h1);

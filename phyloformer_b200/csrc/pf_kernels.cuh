@@ -494,7 +494,7 @@ __device__ __forceinline__ void rt_wait(uint32_t bar, uint32_t parity, int* err_
   for (uint32_t spin = 0; !ok && spin < (1u << 22); ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 1000;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2" PF_WAIT_HINT_STR ";\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(bar), "r"(parity)

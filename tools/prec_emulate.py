@@ -10,7 +10,8 @@ reference outputs -- the question a new `precision` mode has to answer before a 
 
 Operand formats:  x3 = bf16 hi + bf16 lo (16 mantissa bits),  f16 = one fp16 rounding,
 f16x2 = fp16 hi + fp16 lo,  bf16 = one bf16 rounding,  exact = fp64.
-A mode is  <A1>/<W1>/<H>/<W2>,  e.g. the shipped parity mode is  x3/x3/x3/x3  (lo.lo dropped).
+A mode is  <A1>/<W1>/<H>/<W2>,  e.g. the shipped parity mode is  x3/x3/x3/x3  (lo.lo dropped);
+the suffix +fold63 moves the first bias into the GEMM through the redundant LayerNorm channel.
 Test infrastructure: imports oracle/ (allowed for tools and tests only).
 """
 import os
@@ -60,7 +61,8 @@ def qlinear(a, w, fa, fw):
 
 
 def forward(w, x, mode, dtype=torch.float64):
-    fa1, fw1, fh, fw2 = mode.split("/")
+    fold63 = mode.endswith("+fold63")
+    fa1, fw1, fh, fw2 = mode.replace("+fold63", "").split("/")
     x = x.to(dtype)
     B, C, L, n = x.shape
     We = w["embedding_block.0.weight"].to(dtype).reshape(O.D, O.N_CHAR)
@@ -79,7 +81,17 @@ def forward(w, x, mode, dtype=torch.float64):
         W1 = w[p + "ffn.0.weight"].to(dtype).reshape(4 * O.D, O.D)
         W2 = w[p + "ffn.3.weight"].to(dtype).reshape(O.D, 4 * O.D)
         b1 = w[p + "ffn.0.bias"].to(dtype) + W1 @ bt
-        hid = F.gelu(qlinear(nrm, W1 * g, fa1, fw1) + b1)
+        if fold63:
+            # sum_c n_c = 0, so channel 63 is redundant: W1'[:, c] = W1[:, c] - W1[:, 63] (c < 63) gives the same product,
+            # and the freed operand column carries the constant 1 against W1'[:, 63] = b1 (the bias rides on the GEMM)
+            Wp = (W1 * g).clone()
+            Wp[:, :63] -= Wp[:, 63:64].clone()
+            Wp[:, 63] = b1
+            a = nrm.clone()
+            a[..., 63] = 1.0
+            hid = F.gelu(qlinear(a, Wp, fa1, fw1))
+        else:
+            hid = F.gelu(qlinear(nrm, W1 * g, fa1, fw1) + b1)
         h = h + qlinear(hid, W2, fh, fw2) + w[p + "ffn.3.bias"].to(dtype)
     z = F.linear(h, w["pwFNN.0.weight"].to(dtype).reshape(1, O.D), w["pwFNN.0.bias"].to(dtype))
     return F.softplus(z[..., 0]).mean(dim=-1)
