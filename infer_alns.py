@@ -189,7 +189,9 @@ def run_pipeline(model, paths, out_dir, nj, max_tokens, progress=lambda k: None,
     # Parsing stays on this thread: it is one C pass per file (pf_parse_fasta, ~40 us for 20 x 200)
     # and every device call below is asynchronous, so the GPU works on batch k while this loop
     # parses batch k+1; a parse pool only added GIL hand-offs (measured 0.23 vs 0.04 ms per file).
-    with ThreadPoolExecutor(max(1, min(4, n_cpu))) as write_pool:
+    # text formatting needs ~4 writer threads; tree building (host-side C, no GIL; ~30 ms per 100-taxon BME tree)
+    # gets up to 8 so that the GPU stays the slower side
+    with ThreadPoolExecutor(max(1, min(8 if (nj is not None or bme is not None) else 4, n_cpu))) as write_pool:
         buckets = {}
         for alnpath in paths:
             idx, ids = load_alignment_idx(alnpath)
