@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--L", type=int, default=500)
     ap.add_argument("--files", type=int, default=64)
     ap.add_argument("--trees", action="store_true")
+    ap.add_argument("--bme", action="store_true", help="also build the BME (FastME-equivalent) trees: infer_alns.py -b")
     a = ap.parse_args()
     rng = np.random.default_rng(7)
     with tempfile.TemporaryDirectory() as tmp:
@@ -46,7 +47,7 @@ def main():
         os.makedirs(src)
         for k in range(a.files):
             write_fasta(os.path.join(src, f"aln{k:05d}.fa"), a.n, a.L, rng)
-        argv = [a.weights, src, "-o", dst] + (["-t"] if a.trees else [])
+        argv = [a.weights, src, "-o", dst] + (["-t"] if a.trees else []) + (["-b"] if a.bme else [])
         times = []
         for _ in range(2):
             t0 = time.perf_counter()
@@ -54,7 +55,7 @@ def main():
             times.append(time.perf_counter() - t0)
         n_out = len([f for f in os.listdir(dst) if f.endswith(".phy")])
     print(json.dumps({"metric": "cli_msas_per_s", "value": a.files / times[1], "n": a.n, "L": a.L, "files": a.files,
-                      "trees": a.trees, "first_run_s": times[0], "second_run_s": times[1], "phy_written": n_out}))
+                      "trees": a.trees, "bme_trees": a.bme, "first_run_s": times[0], "second_run_s": times[1], "phy_written": n_out}))
 
 
 if __name__ == "__main__":
