@@ -154,7 +154,7 @@ long long pf_neighbor_joining(const float* dm_host, int n, const char* const* na
 #define PF_TREE_NNI 1
 #define PF_TREE_SPR 2
 #define PF_TREE_NJ_START 4
-#define PF_BME_MAX_TAXA 2000
+#define PF_BME_MAX_TAXA 1000
 long long pf_bme_tree(const double* dm_host, int n, const char* const* names, int flags, char* out,
                       long long cap, double* stats);
 

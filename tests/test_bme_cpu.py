@@ -156,6 +156,8 @@ def test_small_and_degenerate_inputs():
         bme_tree(np.zeros((3, 3)), ["a", "b"])
     with pytest.raises(_cabi.PfError):
         bme_tree(np.full((3, 3), np.nan), ["a", "b", "c"])
+    with pytest.raises(_cabi.PfError, match="exceed the limit"):      # PF_BME_MAX_TAXA: the n^2 table is refused, not attempted
+        bme_tree(np.zeros((1001, 1001)), [str(i) for i in range(1001)])
 
 
 def test_nj_start_tree_option():
