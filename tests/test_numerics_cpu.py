@@ -58,3 +58,38 @@ def test_bf16x3_split_product_error():
     e3 = ((three - exact).abs() / scale).max().item()
     e1 = ((one - exact).abs() / scale).max().item()
     assert e3 < 2.0 ** -15 and e1 > 20 * e3, (e3, e1)
+
+
+def test_bias_fold_through_the_redundant_layernorm_channel():
+    """WS_FOLD63 (pf_ffn_ws.cuh / pf_pack_ffn_tc): LayerNorm output sums to zero over its 64 channels, so
+    W u + b == W' u' with W'[:, c] = W[:, c] - W[:, 63] (c < 63), W'[:, 63] = b and u' = u with channel 63 set to 1.
+    Exact in exact arithmetic; with bf16 hi/lo operands (three-term product) the error stays at the split's level."""
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2048, 64, generator=g, dtype=torch.float64) * 3 + torch.randn(2048, 1, generator=g, dtype=torch.float64)
+    u = torch.nn.functional.layer_norm(x, (64,), None, None, 1e-5)
+    assert u.sum(-1).abs().max() < 1e-12
+    w = torch.randn(256, 64, generator=g, dtype=torch.float64) * 0.2
+    b = torch.randn(256, generator=g, dtype=torch.float64)
+    wf = w.clone()
+    wf[:, :63] -= w[:, 63:64]
+    wf[:, 63] = b
+    uf = u.clone()
+    uf[:, 63] = 1.0
+    exact = u @ w.T + b
+    assert (uf @ wf.T - exact).abs().max() < 1e-12
+
+    def split(t):
+        t32 = t.to(torch.float32)
+        hi = t32.to(torch.bfloat16).to(torch.float32)
+        lo = (t32 - hi).to(torch.bfloat16).to(torch.float32)
+        return hi.double(), lo.double()
+
+    def three(a, m):
+        ah, al = split(a)
+        mh, ml = split(m)
+        return ah @ mh.T + ah @ ml.T + al @ mh.T
+
+    scale = u.abs() @ w.abs().T + b.abs()
+    e_plain = ((three(u, w) + b - exact).abs() / scale).max().item()
+    e_fold = ((three(uf, wf) - exact).abs() / scale).max().item()
+    assert e_plain < 2.0 ** -15 and e_fold < 2.0 ** -14, (e_plain, e_fold)     # the folded weights are ~sqrt(2) larger
